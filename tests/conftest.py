@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "slow: longer-running CPU test")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def decode_golden():
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "decode_golden.npz")
+    z = np.load(path)
+    scenes = {}
+    for name in z["names"]:
+        name = str(name)
+        scenes[name] = {
+            "heat": z[f"{name}/heat"], "paf": z[f"{name}/paf"],
+            "hw": tuple(int(v) for v in z[f"{name}/hw"]),
+            "joint_list": z[f"{name}/joint_list"],
+            "limbs": [z[f"{name}/limb{t}"] for t in range(13)],
+            "persons": z[f"{name}/persons"], "joints": z[f"{name}/joints"],
+        }
+    return scenes, {"thre1": float(z["thre"][0]), "thre2": float(z["thre"][1])}
