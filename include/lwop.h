@@ -1,0 +1,187 @@
+/*
+ * lwop.h -- C ABI of the B200-native lightweight_openpose inference hot path.
+ *
+ * The reference (murdockhou/lightweight_openpose) has no FFI: its boundary is
+ * the Python function API
+ *     lightweight_openpose(inputs, num_joints, num_pafs, is_training)   reference src/lightweight_openpose.py:8,48
+ *     conv / conv_dw / conv_dw_no_bn / RefinementStageBlock             reference src/net_factory.py:4,14,23,33
+ *     decode_pose(img_orig, param, heatmaps, pafs)                      reference src/pose_decode.py:460,517
+ * driven by test&eval/model_test.py:42,68,71 (sess.run + decode per frame).
+ * The Python package lightweight_openpose_b200.src mirrors those functions and
+ * binds the entry points below with ctypes.
+ *
+ * Conventions
+ *  - plain C types only; every pointer argument marked "dev" is a CUDA device
+ *    pointer on the handle's device, "host" is ordinary (ideally pinned) memory;
+ *  - tensors are NHWC, kernels arrive pre-folded as [Cout][kh*kw][Cin] float32;
+ *  - every function returns 0 (LWOP_OK) or a negative error code and never
+ *    throws; lwop_last_error() returns a human-readable message for the last
+ *    failure on that handle (or the last global failure when handle is NULL);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *    stream); calls on one handle must be serialised by the caller;
+ *  - the caller owns every input and output buffer; the handle owns weights,
+ *    the activation arena, TMA descriptors and CUDA graphs.
+ */
+#ifndef LWOP_H_
+#define LWOP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LWOP_ABI_VERSION 1
+
+/* error codes */
+#define LWOP_OK                 0
+#define LWOP_ERR_INVALID       -1   /* bad argument */
+#define LWOP_ERR_CUDA          -2   /* CUDA runtime / driver failure */
+#define LWOP_ERR_NO_WEIGHTS    -3   /* forward called before lwop_load_weights */
+#define LWOP_ERR_OVERFLOW      -4   /* a decode table capacity was exceeded */
+#define LWOP_ERR_UNSUPPORTED   -5   /* shape / mode not supported by the kernels */
+#define LWOP_ERR_NO_DEVICE     -6   /* no sm_100 device */
+
+/* arithmetic mode of the forward: bf16 tensor-core path, or the fp32 check path
+ * (CUDA-core fp32, used to bound the bf16 error: BASELINE.json tolerances) */
+#define LWOP_MODE_BF16         0
+#define LWOP_MODE_FP32_CHECK   1
+#define LWOP_MODE_BF16_DIRECT  2   /* bf16 storage, CUDA-core kernels: debugging ladder for the tcgen05 path */
+
+#define LWOP_ACT_NONE 0
+#define LWOP_ACT_RELU 1            /* tf.nn.relu, net_factory.py:11,19 */
+#define LWOP_ACT_ELU  2            /* tf.nn.elu,  net_factory.py:29   */
+
+#define LWOP_DT_F32   0
+#define LWOP_DT_BF16  1
+
+/* lwop_create flags */
+#define LWOP_FLAG_NO_GRAPH   1u    /* launch kernels directly instead of replaying a CUDA graph */
+
+/* network constants (reference src/train_config.py:25-26,31) */
+#define LWOP_NUM_JOINTS   14
+#define LWOP_NUM_PAFS     26
+#define LWOP_NUM_LIMBS    13
+#define LWOP_STRIDE        8
+
+/* decode table capacities (per image) */
+#define LWOP_MAX_PEAKS    128      /* peaks per joint channel */
+#define LWOP_MAX_JOINTS  1792      /* 14 * 128 rows of the joint list */
+#define LWOP_MAX_PERSONS  128
+#define LWOP_COUNTS        32      /* int32 slots per image, see below */
+/* counts[b][0] = rows in the joint list, [1] = persons, [2] = overflow bitmask
+ * (1: peaks/channel, 2: persons, 4: candidates), [3] = total connections,
+ * [4..17] = peaks per joint channel, [18..30] = connections per limb type */
+
+typedef struct lwop_handle lwop_handle;
+
+int         lwop_abi_version(void);
+const char *lwop_error_string(int code);
+const char *lwop_last_error(const lwop_handle *h);
+
+/* Replaces graph construction: tf.placeholder + lightweight_openpose(...) in
+ * test&eval/model_test.py:39-42.  The handle is sized for images up to
+ * [max_batch, height, width, 3]; smaller batches may be passed to lwop_forward. */
+int lwop_create(int device, int max_batch, int height, int width, unsigned flags, lwop_handle **out);
+int lwop_destroy(lwop_handle *h);
+
+/* Replaces tf.train.Saver().restore (test&eval/model_test.py:43,49).  `blob` is
+ * the float32 concatenation produced by lightweight_openpose_b200.graph.pack_blob
+ * (per layer: depthwise [9][Cin] if separable, kernel [Cout][taps][Cin] with BN
+ * folded, bias [Cout]); its length must equal lwop_weights_num_floats(). */
+size_t lwop_weights_num_floats(void);
+int    lwop_load_weights(lwop_handle *h, const float *host_blob, size_t num_floats);
+
+/* Replaces sess.run([cpm, paf], feed_dict) (test&eval/model_test.py:68,92).
+ * in_dev: [batch, H, W, 3] float32 RGB in [0,1];  heat_dev: [batch, H/8, W/8, 14]
+ * float32;  paf_dev: [batch, H/8, W/8, 26] float32.  stage1_heat_dev/stage1_paf_dev
+ * are optional (NULL) outputs of the initial stage (lightweight_openpose.py:32-35). */
+int lwop_forward(lwop_handle *h, const float *in_dev, int batch, int mode,
+                 float *heat_dev, float *paf_dev,
+                 float *stage1_heat_dev, float *stage1_paf_dev, void *stream);
+
+/* Same, from uint8 frames: does the reference's `img / 255.` (model_test.py:65)
+ * on the device.  in_dev: [batch, H, W, 3] uint8 RGB. */
+int lwop_forward_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int mode,
+                    float *heat_dev, float *paf_dev, void *stream);
+
+/* Decode tables, caller-allocated device memory (sizes for `batch` images):
+ *   counts    int32  [batch][LWOP_COUNTS]
+ *   joints    double [batch][LWOP_MAX_JOINTS][6]   (x, y, score, id, 0, joint_type)   pose_decode.py:481-482
+ *   limbs     double [batch][13][LWOP_MAX_PEAKS][5] (src_id, dst_id, score, i, j)     pose_decode.py:287
+ *   persons   double [batch][LWOP_MAX_PERSONS][16]                                    pose_decode.py:369-379
+ *   keypoints float  [batch][LWOP_MAX_PERSONS][42]                                    pose_decode.py:403,516 */
+typedef struct lwop_decode_tables {
+    int32_t *counts;
+    double  *joints;
+    double  *limbs;
+    double  *persons;
+    float   *keypoints;
+} lwop_decode_tables;
+
+/* Replaces decode_pose (src/pose_decode.py:460-517) minus the canvas drawing,
+ * batched.  heat_dev [batch,h,w,14], paf_dev [batch,h,w,26] float32; image size
+ * (img_h, img_w) gives the up-sampling factor img_h / h exactly as :462 does.
+ * Returns LWOP_ERR_OVERFLOW only after a later lwop_decode_status(). */
+int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int batch,
+                int map_h, int map_w, int img_h, int img_w, float thre1, double thre2,
+                const lwop_decode_tables *tables_dev, void *stream);
+
+/* Host-side result of lwop_infer_host / lwop_decode_fetch: rows of all images
+ * concatenated in image order (per image: counts[b][0] joint rows, counts[b][1]
+ * person / keypoint rows, counts[b][18+t] limb rows per limb type t in order). */
+typedef struct lwop_packed_tables {
+    int32_t *counts;        /* [batch][LWOP_COUNTS] */
+    double  *joints;        /* [joints_cap][6]  */
+    double  *limbs;         /* [limbs_cap][5]   */
+    double  *persons;       /* [persons_cap][16] */
+    float   *keypoints;     /* [persons_cap][42] */
+    size_t   joints_cap, limbs_cap, persons_cap;   /* capacities in rows */
+} lwop_packed_tables;
+
+/* Compacts device tables produced by lwop_decode and copies them to the host
+ * (two device->host phases: counts, then exactly the used rows).  Synchronises
+ * `stream`.  Returns LWOP_ERR_OVERFLOW if a capacity (device table or host
+ * buffer) was exceeded. */
+int lwop_decode_fetch(lwop_handle *h, const lwop_decode_tables *tables_dev, int batch,
+                      const lwop_packed_tables *out_host, void *stream);
+
+/* Whole path with HOST buffers in one call (what model_test.py's loop body does
+ * per frame, batched): H2D of the frames, forward, decode, D2H of the compacted
+ * result tables.  images_host: [batch,H,W,3] float32 (or uint8 when is_u8).
+ * heat_host / paf_host may be NULL when the maps themselves are not wanted.
+ * Synchronises `stream` before returning. */
+int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode,
+                    float thre1, double thre2, const lwop_packed_tables *out_host,
+                    float *heat_host, float *paf_host, void *stream);
+
+/* ---- per-op entries mirroring src/net_factory.py (unit tests, eager mode) ---- */
+
+/* conv(): dense conv2d 'same' + bias + activation (+ residual added after the
+ * activation, tf.add in net_factory.py:37 / lightweight_openpose.py:27).
+ * w_dev float32 [Cout][k*k][Cin], bias_dev float32 [Cout] or NULL. */
+int lwop_conv2d(lwop_handle *h, int mode, const void *in_dev, int in_dtype,
+                int batch, int height, int width, int cin,
+                const float *w_dev, const float *bias_dev, int cout, int ksize, int stride, int dilation,
+                int act, const void *residual_dev, void *out_dev, int out_dtype, void *stream);
+
+/* depthwise half of tf.layers.separable_conv2d (net_factory.py:15,25):
+ * 3x3, channel multiplier 1, 'same', no bias, no activation.  w_dev float32 [9][C]. */
+int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype,
+                      int batch, int height, int width, int channels,
+                      const float *w_dev, int stride, int dilation, void *out_dev, void *stream);
+
+/* output size of a 'same' conv: ceil(in / stride) */
+int lwop_same_out(int in, int stride);
+
+/* CRC32C (Castagnoli) for TensorBundle verification; host function. */
+uint32_t lwop_crc32c(const void *data, size_t nbytes);
+
+/* number of kernel launches issued by this handle since creation / last reset */
+long long lwop_launch_count(const lwop_handle *h, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWOP_H_ */

@@ -1,0 +1,199 @@
+// Shared device/host helpers for the lwop kernels (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lwop.h"
+
+namespace lwop {
+
+// ---------------------------------------------------------------------------
+// TF 'SAME' padding (reference net_factory.py:6,16,26 pass padding='same'):
+// out = ceil(in/stride); total = max((out-1)*stride + (k-1)*dil + 1 - in, 0);
+// the smaller half goes before.
+// ---------------------------------------------------------------------------
+struct SamePad {
+    int out, before;
+};
+__host__ __device__ inline SamePad same_pad(int in, int k, int stride, int dil) {
+    SamePad p;
+    p.out = (in + stride - 1) / stride;
+    int total = (p.out - 1) * stride + (k - 1) * dil + 1 - in;
+    if (total < 0) total = 0;
+    p.before = total / 2;
+    return p;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == LWOP_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == LWOP_ACT_ELU) return v > 0.0f ? v : expm1f(v);
+    return v;
+}
+
+// element load/store as float for the two storage types
+__device__ __forceinline__ float ld_as_float(const float *p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_from_float(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA, tcgen05 (see /opt/skills/guides/blackwell_cuda_programming.md)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap (-> CUDA error the host reports)
+// instead of hanging the GPU box.  ~2^26 probes of a HW-sleeping try_wait is
+// several seconds, far beyond any legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("lwop: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void *desc) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+// 2D tiled load: coordinates (c0 = innermost, c1)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *desc, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 4D tiled load: coordinates (c, w, h, n)
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const void *desc, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+// 4D im2col load: base pixel (c, w, h, n) inside the bounding box + filter offsets (w, h)
+__device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, const void *desc, uint64_t *bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w),
+        "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
+// ---- tcgen05 ----
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; one thread issues.
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread complete
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i = lane i)
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor for a tile whose rows are `kSwizzleBytes`
+// wide (one swizzle atom: 8 rows x kSwizzleBytes, atoms stacked along M/N every
+// 8*kSwizzleBytes bytes).  Bit layout per the tcgen05 matrix-descriptor format:
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,
+// [46,48) version = 1, [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B).
+template <int kSwizzleBytes>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = kSwizzleBytes == 128 ? 2 : (kSwizzleBytes == 64 ? 4 : 6);
+    constexpr uint64_t sbo = (8 * kSwizzleBytes) >> 4;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;   // LBO (ignored for swizzled K-major; canonical value 1)
+    d |= sbo << 32;
+    d |= static_cast<uint64_t>(1) << 46;   // descriptor version (Blackwell)
+    d |= layout << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16 with bf16 A/B (K-major), fp32 D.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
+    return (1u << 4)               // D format: F32
+           | (1u << 7)             // A format: BF16
+           | (1u << 10)            // B format: BF16
+           | (0u << 15)            // A K-major
+           | (0u << 16)            // B K-major
+           | ((n >> 3) << 17)      // N >> 3
+           | ((m >> 4) << 24);     // M >> 4
+}
+
+}  // namespace lwop

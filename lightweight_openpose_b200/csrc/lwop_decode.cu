@@ -1,0 +1,602 @@
+// On-device pose decode, batched over images.  Restates the observable
+// behaviour of the reference src/pose_decode.py:
+//   K1 peaks_kernel   : find_peaks_v2 (:52-76) + patch refinement of NMS (:107-185)
+//   K2 limbs_kernel   : find_connected_joints (:188-301) with the PAF bicubic
+//                       up-sampling of decode_pose (:487) evaluated on the fly
+//   K3 group_kernel   : joint list (:481-482), group_limbs_of_same_person (:304-396),
+//                       keypoint table of plot_pose (:403-429)
+//   K4 pack_kernel    : compaction of the per-image tables for the host copy
+// All float arithmetic that feeds an integer decision uses explicit _rn
+// intrinsics so the compiler cannot contract it into FMAs: the sequence of
+// roundings is the one of the numpy/cv2 code (float32 two-pass bicubic,
+// float64 limb scores).
+#include "lwop_kernels.cuh"
+
+namespace lwop {
+
+namespace {
+
+__constant__ int c_limb_src[13] = {0, 1, 3, 4, 6, 7, 9, 10, 12, 13, 13, 13, 13};   // pose_decode.py:17-18
+__constant__ int c_limb_dst[13] = {1, 2, 4, 5, 7, 8, 10, 11, 13, 0, 3, 6, 9};
+
+constexpr int kRadius = 5;          // dis_thres, pose_decode.py:53
+constexpr int kPatchHalf = 2;       // win_size,  pose_decode.py:141
+constexpr int kSamples = 10;        // num_intermed_pts, pose_decode.py:188
+constexpr int kMaxPixPerThread = 64;
+
+// cv2 interpolateCubic, A = -0.75, float32, no contraction
+__device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
+    const float A = -0.75f;
+    const float x1 = __fadd_rn(x, 1.0f);
+    // ((A*(x+1) - 5A)*(x+1) + 8A)*(x+1) - 4A
+    float t = __fsub_rn(__fmul_rn(A, x1), __fmul_rn(5.0f, A));
+    t = __fadd_rn(__fmul_rn(t, x1), __fmul_rn(8.0f, A));
+    c[0] = __fsub_rn(__fmul_rn(t, x1), __fmul_rn(4.0f, A));
+    // ((A+2)*x - (A+3))*x*x + 1
+    t = __fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), x), __fadd_rn(A, 3.0f));
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(t, x), x), 1.0f);
+    const float xm = __fsub_rn(1.0f, x);
+    t = __fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), xm), __fadd_rn(A, 3.0f));
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(t, xm), xm), 1.0f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, c[0]), c[1]), c[2]);
+}
+
+// source position of destination index d: fx = (float)((d + 0.5) * scale - 0.5)
+__device__ __forceinline__ void src_pos(int d, double scale, int &s, float &frac) {
+    const float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    const float fl = floorf(f);
+    s = (int)fl;
+    frac = __fsub_rn(f, fl);
+}
+
+__device__ __forceinline__ float dot4(const float (&v)[4], const float (&c)[4]) {
+    float r = __fmul_rn(v[0], c[0]);
+    r = __fadd_rn(r, __fmul_rn(v[1], c[1]));
+    r = __fadd_rn(r, __fmul_rn(v[2], c[2]));
+    r = __fadd_rn(r, __fmul_rn(v[3], c[3]));
+    return r;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// cv2 saturate_cast<int>(double) = round half to even
+__device__ __forceinline__ int cv_round(double v) { return (int)rint(v); }
+
+// ---------------------------------------------------------------------------
+// K1: per (image, joint channel): threshold, greedy radius-5 NMS, refinement.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor,
+             float *__restrict__ peaks, int *__restrict__ peak_counts, int *__restrict__ counts) {
+    extern __shared__ unsigned char smem_raw[];
+    const int npix = h * w;
+    float *val = reinterpret_cast<float *>(smem_raw);
+    unsigned char *state = reinterpret_cast<unsigned char *>(val + npix);   // 0 none, 1 undecided, 2 kept, 3 dead
+    __shared__ int s_n;
+    __shared__ int s_list[LWOP_MAX_PEAKS * 4];      // kept pixel indices (unsorted, up to 4x cap before truncation)
+    __shared__ int s_sorted[LWOP_MAX_PEAKS];
+
+    const int ch = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const float *src = heat + (long long)b * npix * C + ch;
+    for (int p = tid; p < npix; p += blockDim.x) {
+        const float v = src[(long long)p * C];
+        val[p] = v;
+        state[p] = v > thre1 ? 1 : 0;               // np.where(img > thre1), pose_decode.py:54
+    }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+
+    // Parallel form of the greedy loop (:62-70): in score order a pixel is kept
+    // iff no already-kept pixel lies within distance 5.  Round: every undecided
+    // pixel that beats all undecided pixels of its disk is kept; then undecided
+    // pixels inside a kept disk die.  Priority = (score, row-major index), larger
+    // first (exact ties: see DESIGN.md).
+    while (true) {
+        unsigned long long keep_mask = 0;
+        int undecided = 0;
+        int slot = 0;
+        for (int p = tid; p < npix; p += blockDim.x, ++slot) {
+            if (state[p] != 1) continue;
+            undecided = 1;
+            const int py = p / w, px = p - py * w;
+            const float v = val[p];
+            bool best = true;
+            for (int dy = -kRadius; dy <= kRadius && best; ++dy) {
+                const int qy = py + dy;
+                if (qy < 0 || qy >= h) continue;
+                for (int dx = -kRadius; dx <= kRadius; ++dx) {
+                    if (dx * dx + dy * dy > kRadius * kRadius || (dx == 0 && dy == 0)) continue;
+                    const int qx = px + dx;
+                    if (qx < 0 || qx >= w) continue;
+                    const int q = qy * w + qx;
+                    if (state[q] != 1) continue;
+                    const float u = val[q];
+                    if (u > v || (u == v && q > p)) { best = false; break; }
+                }
+            }
+            if (best) keep_mask |= 1ull << slot;
+        }
+        if (!__syncthreads_or(undecided)) break;
+        slot = 0;
+        for (int p = tid; p < npix; p += blockDim.x, ++slot)
+            if (keep_mask >> slot & 1ull) state[p] = 2;
+        __syncthreads();
+        for (int p = tid; p < npix; p += blockDim.x) {
+            if (state[p] != 1) continue;
+            const int py = p / w, px = p - py * w;
+            bool dead = false;
+            for (int dy = -kRadius; dy <= kRadius && !dead; ++dy) {
+                const int qy = py + dy;
+                if (qy < 0 || qy >= h) continue;
+                for (int dx = -kRadius; dx <= kRadius; ++dx) {
+                    if (dx * dx + dy * dy > kRadius * kRadius) continue;
+                    const int qx = px + dx;
+                    if (qx < 0 || qx >= w) continue;
+                    if (state[qy * w + qx] == 2) { dead = true; break; }
+                }
+            }
+            if (dead) state[p] = 3;
+        }
+        __syncthreads();
+    }
+
+    // gather kept pixels, rank them by priority (kept order of the reference = descending score)
+    for (int p = tid; p < npix; p += blockDim.x)
+        if (state[p] == 2) {
+            const int i = atomicAdd(&s_n, 1);
+            if (i < LWOP_MAX_PEAKS * 4) s_list[i] = p;
+        }
+    __syncthreads();
+    const int n_all = min(s_n, LWOP_MAX_PEAKS * 4);
+    const int n = min(n_all, LWOP_MAX_PEAKS);
+    for (int i = tid; i < n_all; i += blockDim.x) {
+        const int p = s_list[i];
+        const float v = val[p];
+        int rank = 0;
+        for (int j = 0; j < n_all; ++j) {
+            const int q = s_list[j];
+            const float u = val[q];
+            rank += (u > v || (u == v && q > p)) ? 1 : 0;
+        }
+        if (rank < LWOP_MAX_PEAKS) s_sorted[rank] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        peak_counts[b * 16 + ch] = n;
+        if (s_n > LWOP_MAX_PEAKS) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
+    }
+
+    // refinement (:148-183): bicubic up-sampling of the clipped 5x5 patch by `factor`,
+    // argmax (first maximum in row-major order), one warp per peak
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const double scale = 1.0 / factor;              // cv2: scale_x = 1. / inv_scale_x
+    for (int i = warp; i < n; i += nwarps) {
+        const int p = s_sorted[i];
+        const int py = p / w, px = p - py * w;
+        const int x0 = max(0, px - kPatchHalf), y0 = max(0, py - kPatchHalf);
+        const int x1 = min(w - 1, px + kPatchHalf), y1 = min(h - 1, py + kPatchHalf);
+        const int pw = x1 - x0 + 1, ph = y1 - y0 + 1;
+        const int dw = cv_round((double)pw * factor), dh = cv_round((double)ph * factor);
+        float best_v = -INFINITY;
+        int best_i = 0x7fffffff;
+        for (int d = lane; d < dw * dh; d += 32) {
+            const int oy = d / dw, ox = d - oy * dw;
+            int sx, sy;
+            float fx, fy, cx[4], cy[4];
+            src_pos(ox, scale, sx, fx);
+            src_pos(oy, scale, sy, fy);
+            cubic_coeffs(fx, cx);
+            cubic_coeffs(fy, cy);
+            float rows[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int yy = y0 + clampi(sy - 1 + r, 0, ph - 1);
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k] = val[yy * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
+                rows[r] = dot4(t, cx);
+            }
+            const float v = dot4(rows, cy);
+            if (v > best_v) { best_v = v; best_i = d; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        }
+        if (lane == 0) {
+            const int my = best_i / dw, mx = best_i - my * dw;
+            // floor( resized(peak) + (argmax - resized(peak - patch_origin)) ), float64 (:171-182, :104)
+            const double cxp = __dsub_rn(__dmul_rn(__dadd_rn((double)(px - x0), 0.5), factor), 0.5);
+            const double cyp = __dsub_rn(__dmul_rn(__dadd_rn((double)(py - y0), 0.5), factor), 0.5);
+            const double ax = __dsub_rn(__dmul_rn(__dadd_rn((double)px, 0.5), factor), 0.5);
+            const double ay = __dsub_rn(__dmul_rn(__dadd_rn((double)py, 0.5), factor), 0.5);
+            const double rx = floor(__dadd_rn(ax, __dsub_rn((double)mx, cxp)));
+            const double ry = floor(__dadd_rn(ay, __dsub_rn((double)my, cyp)));
+            float *o = peaks + (((long long)b * LWOP_NUM_JOINTS + ch) * LWOP_MAX_PEAKS + i) * 4;
+            o[0] = (float)rx;
+            o[1] = (float)ry;
+            o[2] = best_v;
+            o[3] = 0.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bicubic sample of one PAF channel at full-resolution pixel (X, Y): what
+// cv2.resize(pafs, (W, H), INTER_CUBIC)[Y, X, c] holds (pose_decode.py:487).
+// ---------------------------------------------------------------------------
+struct AxisTaps {
+    int idx[4];
+    float c[4];
+};
+__device__ __forceinline__ AxisTaps axis_taps(int d, double scale, int n) {
+    AxisTaps t;
+    int s;
+    float f;
+    src_pos(d, scale, s, f);
+    cubic_coeffs(f, t.c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t.idx[k] = clampi(s - 1 + k, 0, n - 1);
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// K2: per (image, limb type): score every (src, dst) joint pair, keep per src
+// the best dst.  One warp per src joint, lanes over dst joints.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double thre2,
+             const float *__restrict__ peaks, const int *__restrict__ peak_counts, double *__restrict__ limbs,
+             int *__restrict__ counts) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int ja = c_limb_src[t], jb = c_limb_dst[t];
+    const int *pc = peak_counts + b * 16;
+    const int na = pc[ja], nb = pc[jb];
+    __shared__ int s_rows;
+    __shared__ unsigned char s_has[LWOP_MAX_PEAKS];
+    __shared__ double s_score[LWOP_MAX_PEAKS];
+    __shared__ int s_j[LWOP_MAX_PEAKS];
+    if (threadIdx.x == 0) s_rows = 0;
+    for (int i = threadIdx.x; i < LWOP_MAX_PEAKS; i += blockDim.x) s_has[i] = 0;
+    __syncthreads();
+    double *out = limbs + ((long long)b * LWOP_NUM_LIMBS + t) * LWOP_MAX_PEAKS * 5;
+    if (na == 0 || nb == 0) {                                     // (:224-228)
+        if (threadIdx.x == 0) counts[b * LWOP_COUNTS + 18 + t] = 0;
+        return;
+    }
+    int ida = 0, idb = 0;                                         // unique ids count channels then peaks (:135,183)
+    for (int c = 0; c < ja; ++c) ida += pc[c];
+    for (int c = 0; c < jb; ++c) idb += pc[c];
+    const float *pa = peaks + ((long long)b * LWOP_NUM_JOINTS + ja) * LWOP_MAX_PEAKS * 4;
+    const float *pb = peaks + ((long long)b * LWOP_NUM_JOINTS + jb) * LWOP_MAX_PEAKS * 4;
+    const float *pafb = paf + (long long)b * h * w * LWOP_NUM_PAFS;
+    const int cx_ch = 2 * t, cy_ch = 2 * t + 1;                   // paf_xy_coords_per_limb (:23-24)
+    const double scale_x = 1.0 / ((double)W / (double)w);         // cv2: 1. / (dsize / ssize)
+    const double scale_y = 1.0 / ((double)H / (double)h);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+    for (int i = warp; i < na; i += nwarps) {
+        const double ax = pa[i * 4 + 0], ay = pa[i * 4 + 1];
+        double best = 0.0;                                        // best_score = 0.0 (:243)
+        int best_j = 0x7fffffff;
+        for (int j = lane; j < nb; j += 32) {
+            const double bx = pb[j * 4 + 0], by = pb[j * 4 + 1];
+            const double dx = bx - ax, dy = by - ay;              // limb_dir (:249)
+            if (fabs(dx) > (double)W || fabs(dy) > (double)H) continue;   // (:209,250)
+            const double norm = __dadd_rn(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), 1e-8);   // (:255)
+            const double ux = dx / norm, uy = dy / norm;
+            const double stepx = dx / 9.0, stepy = dy / 9.0;      // np.linspace(start, stop, 10)
+            double s[kSamples];
+            int above = 0;
+#pragma unroll
+            for (int k = 0; k < kSamples; ++k) {
+                double fxk = k == kSamples - 1 ? bx : __dadd_rn(__dmul_rn((double)k, stepx), ax);
+                double fyk = k == kSamples - 1 ? by : __dadd_rn(__dmul_rn((double)k, stepy), ay);
+                int X = (int)rint(fxk), Y = (int)rint(fyk);       // np.round: half to even (:260-264)
+                X = clampi(X, 0, W - 1);                          // joints are inside the frame; guard only
+                Y = clampi(Y, 0, H - 1);
+                const AxisTaps tx = axis_taps(X, scale_x, w), ty = axis_taps(Y, scale_y, h);
+                float rx[4], ry[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float *row = pafb + (long long)ty.idx[r] * w * LWOP_NUM_PAFS;
+                    float vx[4], vy[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 v = *reinterpret_cast<const float2 *>(row + tx.idx[q] * LWOP_NUM_PAFS + cx_ch);
+                        vx[q] = v.x;
+                        vy[q] = v.y;
+                    }
+                    rx[r] = dot4(vx, tx.c);
+                    ry[r] = dot4(vy, tx.c);
+                }
+                const double px = (double)dot4(rx, ty.c), py = (double)dot4(ry, ty.c);
+                s[k] = __dadd_rn(__dmul_rn(px, ux), __dmul_rn(py, uy));   // intermed_paf.dot(limb_dir) (:270)
+                above += s[k] > thre2 ? 1 : 0;
+            }
+            // numpy pairwise mean of 10 float64 values (:271)
+            double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
+                                   __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
+            sum = __dadd_rn(__dadd_rn(sum, s[8]), s[9]);
+            const double mean = sum / 10.0;
+            if (above > 8 && mean > thre2 && mean > best) {       // criteria (:276-285); first j wins ties
+                best = mean;
+                best_j = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+            if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+        }
+        if (lane == 0 && best_j != 0x7fffffff) {
+            s_has[i] = 1;
+            s_score[i] = best;
+            s_j[i] = best_j;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                       // rows in src order (:297)
+        int r = 0;
+        for (int i = 0; i < na; ++i)
+            if (s_has[i]) {
+                double *o = out + r * 5;
+                o[0] = (double)(ida + i);
+                o[1] = (double)(idb + s_j[i]);
+                o[2] = s_score[i];
+                o[3] = (double)i;
+                o[4] = (double)s_j[i];
+                ++r;
+            }
+        counts[b * LWOP_COUNTS + 18 + t] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: per image (one warp): joint list, greedy grouping, keypoint table.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_counts, const double *__restrict__ limbs,
+             int *__restrict__ counts, double *__restrict__ joints, double *__restrict__ persons,
+             float *__restrict__ keypoints) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    __shared__ double P[LWOP_MAX_PERSONS][16];
+    __shared__ int s_off[LWOP_NUM_JOINTS + 1];
+    const int *pc = peak_counts + b * 16;
+    int *cnt = counts + b * LWOP_COUNTS;
+    if (lane == 0) {
+        int acc = 0;
+        for (int c = 0; c < LWOP_NUM_JOINTS; ++c) {
+            s_off[c] = acc;
+            cnt[4 + c] = pc[c];
+            acc += pc[c];
+        }
+        s_off[LWOP_NUM_JOINTS] = acc;
+        cnt[0] = acc;
+    }
+    __syncwarp();
+    double *jl = joints + (long long)b * LWOP_MAX_JOINTS * 6;
+    for (int c = 0; c < LWOP_NUM_JOINTS; ++c) {                   // (x, y, score, id, 0, type) (:481-482)
+        const float *pk = peaks + ((long long)b * LWOP_NUM_JOINTS + c) * LWOP_MAX_PEAKS * 4;
+        for (int i = lane; i < pc[c]; i += 32) {
+            double *o = jl + (long long)(s_off[c] + i) * 6;
+            o[0] = pk[i * 4 + 0];
+            o[1] = pk[i * 4 + 1];
+            o[2] = pk[i * 4 + 2];
+            o[3] = (double)(s_off[c] + i);
+            o[4] = 0.0;
+            o[5] = (double)c;
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    int np = 0, total_conn = 0;
+    bool overflow = false;
+    for (int t = 0; t < LWOP_NUM_LIMBS; ++t) {
+        const int ja = c_limb_src[t], jb = c_limb_dst[t];
+        const int nconn = cnt[18 + t];
+        total_conn += nconn;
+        const double *rows = limbs + ((long long)b * LWOP_NUM_LIMBS + t) * LWOP_MAX_PEAKS * 5;
+        for (int r = 0; r < nconn; ++r) {
+            const double a_id = rows[r * 5 + 0], b_id = rows[r * 5 + 1], s = rows[r * 5 + 2];
+            // persons that already hold one of the two joints (:329-331)
+            int nm = 0, m0 = -1, m1 = -1;
+            for (int base = 0; base < np; base += 32) {
+                const int k = base + lane;
+                const bool hit = k < np && (P[k][ja] == a_id || P[k][jb] == b_id);
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int bit = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (nm == 0) m0 = base + bit;
+                    else if (nm == 1) m1 = base + bit;
+                    ++nm;
+                }
+            }
+            const double js_b = jl[(long long)(int)b_id * 6 + 2];
+            if (nm == 1) {                                        // (:336-347)
+                if (lane == 0 && P[m0][jb] != b_id) {
+                    P[m0][jb] = b_id;
+                    P[m0][15] += 1.0;
+                    P[m0][14] += __dadd_rn(js_b, s);
+                }
+            } else if (nm == 2) {                                 // (:348-366)
+                bool share = false;
+                if (lane < 14) share = P[m0][lane] >= 0.0 && P[m1][lane] >= 0.0;
+                share = __any_sync(0xffffffffu, share);
+                if (!share) {
+                    if (lane < 14) P[m0][lane] += __dadd_rn(P[m1][lane], 1.0);
+                    if (lane == 14) P[m0][14] = __dadd_rn(__dadd_rn(P[m0][14], P[m1][14]), s);
+                    if (lane == 15) P[m0][15] += P[m1][15];
+                    __syncwarp();
+                    for (int k = m1; k + 1 < np; ++k) {           // list.pop(m1)
+                        if (lane < 16) P[k][lane] = P[k + 1][lane];
+                        __syncwarp();
+                    }
+                    --np;
+                } else if (lane == 0) {
+                    P[m0][jb] = b_id;
+                    P[m0][15] += 1.0;
+                    P[m0][14] += __dadd_rn(js_b, s);
+                }
+            } else {                                              // 0 or >= 3 matches: new person (:367-379)
+                if (np < LWOP_MAX_PERSONS) {
+                    if (lane < 14) P[np][lane] = lane == ja ? a_id : (lane == jb ? b_id : -1.0);
+                    if (lane == 15) P[np][15] = 2.0;
+                    if (lane == 14) {
+                        const double js_a = jl[(long long)(int)a_id * 6 + 2];
+                        P[np][14] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, js_a), js_b), s);
+                    }
+                    ++np;
+                } else {
+                    overflow = true;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // drop persons with < 3 parts or mean score < 0.2 (:382-391); keypoint table (:403-429)
+    double *po = persons + (long long)b * LWOP_MAX_PERSONS * 16;
+    float *ko = keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
+    int kept = 0;
+    for (int k = 0; k < np; ++k) {
+        const bool drop = P[k][15] < 3.0 || (P[k][14] / P[k][15]) < 0.2;
+        if (drop) continue;
+        if (lane < 16) po[kept * 16 + lane] = P[k][lane];
+        for (int e = lane; e < 42; e += 32) ko[kept * 42 + e] = 0.0f;
+        __syncwarp();
+        if (lane == 0) {
+            for (int t = 0; t < LWOP_NUM_LIMBS; ++t) {
+                const double ia = P[k][c_limb_src[t]], ib = P[k][c_limb_dst[t]];
+                if (ia < 0.0 || ib < 0.0) continue;               // `-1 in joint_indices` (:411)
+                const double ids[2] = {ia, ib};
+                for (int e = 0; e < 2; ++e) {
+                    const double *row = jl + (long long)(int)ids[e] * 6;
+                    const int jt = (int)row[5];
+                    ko[kept * 42 + jt * 3 + 0] = (float)row[0];
+                    ko[kept * 42 + jt * 3 + 1] = (float)row[1];
+                    ko[kept * 42 + jt * 3 + 2] = 1.0f;
+                }
+            }
+        }
+        __syncwarp();
+        ++kept;
+    }
+    if (lane == 0) {
+        cnt[1] = kept;
+        cnt[3] = total_conn;
+        if (overflow) atomicOr(&cnt[2], 2);
+    }
+}
+
+// K4: exclusive prefix over images of (joints, persons, connections), one block
+__global__ void __launch_bounds__(1024)
+pack_offsets_kernel(const int *__restrict__ counts, int B, int *__restrict__ offsets) {
+    __shared__ int s[3][1024];
+    const int tid = threadIdx.x;
+    int carry[3] = {0, 0, 0};
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        const int idx[3] = {0, 1, 3};
+        int v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = b < B ? counts[b * LWOP_COUNTS + idx[k]] : 0;
+            s[k][tid] = v[k];
+        }
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int t[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] = tid >= o ? s[k][tid - o] : 0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s[k][tid] += t[k];
+            __syncthreads();
+        }
+        if (b < B) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) offsets[b * 4 + k] = carry[k] + s[k][tid] - v[k];
+            offsets[b * 4 + 3] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) carry[k] += s[k][1023];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        offsets[B * 4 + 0] = carry[0];
+        offsets[B * 4 + 1] = carry[1];
+        offsets[B * 4 + 2] = carry[2];
+        offsets[B * 4 + 3] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+pack_rows_kernel(lwop_decode_tables t, const int *__restrict__ offsets, double *__restrict__ joints_p,
+                 double *__restrict__ limbs_p, double *__restrict__ persons_p, float *__restrict__ keypoints_p) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int *cnt = t.counts + b * LWOP_COUNTS;
+    const int *off = offsets + b * 4;
+    const int nj = cnt[0], np = cnt[1];
+    const double *js = t.joints + (long long)b * LWOP_MAX_JOINTS * 6;
+    for (int i = tid; i < nj * 6; i += blockDim.x) joints_p[(long long)off[0] * 6 + i] = js[i];
+    const double *ps = t.persons + (long long)b * LWOP_MAX_PERSONS * 16;
+    for (int i = tid; i < np * 16; i += blockDim.x) persons_p[(long long)off[1] * 16 + i] = ps[i];
+    const float *ks = t.keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
+    for (int i = tid; i < np * 42; i += blockDim.x) keypoints_p[(long long)off[1] * 42 + i] = ks[i];
+    long long row = off[2];
+    for (int l = 0; l < LWOP_NUM_LIMBS; ++l) {
+        const int nc = cnt[18 + l];
+        const double *ls = t.limbs + ((long long)b * LWOP_NUM_LIMBS + l) * LWOP_MAX_PEAKS * 5;
+        for (int i = tid; i < nc * 5; i += blockDim.x) limbs_p[row * 5 + i] = ls[i];
+        row += nc;
+    }
+}
+
+__global__ void zero_counts_kernel(int *counts, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = 0;
+}
+
+}  // namespace
+
+size_t decode_scratch_peaks_bytes(int B) {
+    return (size_t)B * LWOP_NUM_JOINTS * LWOP_MAX_PEAKS * 4 * sizeof(float);
+}
+
+cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,
+                               double *limbs_packed, double *persons_packed, float *keypoints_packed,
+                               cudaStream_t s, long long *launches) {
+    pack_offsets_kernel<<<1, 1024, 0, s>>>(t.counts, B, offsets);
+    pack_rows_kernel<<<B, 128, 0, s>>>(t, offsets, joints_packed, limbs_packed, persons_packed, keypoints_packed);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launches) {
+    const int npix = a.h * a.w;
+    if (npix > kMaxPixPerThread * 256) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)npix * 5 + 16;
+    if (smem > 96 * 1024) return cudaErrorInvalidValue;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const int ncounts = a.B * LWOP_COUNTS;
+    zero_counts_kernel<<<(ncounts + 255) / 256, 256, 0, s>>>(a.t.counts, ncounts);
+    const double factor = (double)a.H / (double)a.h;              // scale = img_H / heat_H (:462)
+    peaks_kernel<<<dim3(LWOP_NUM_JOINTS, a.B), 256, smem, s>>>(a.heat, a.h, a.w, LWOP_NUM_JOINTS, a.thre1, factor,
+                                                               a.peaks, a.peak_counts, a.t.counts);
+    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), 128, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, a.peaks,
+                                                           a.peak_counts, a.t.limbs, a.t.counts);
+    group_kernel<<<a.B, 32, 0, s>>>(a.peaks, a.peak_counts, a.t.limbs, a.t.counts, a.t.joints, a.t.persons,
+                                    a.t.keypoints);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+}  // namespace lwop

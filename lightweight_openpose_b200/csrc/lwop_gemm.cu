@@ -1,0 +1,439 @@
+// bf16 implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a):
+//   D[M, N] = act( sum_taps A_tap[M, Cin] * W_tap[N, Cin]^T + bias ) (+ residual)
+// with M = B*H*W output pixels (stride-1 'same' convs), N = Cout.
+//
+//   * operands staged by TMA into 128B/64B-swizzled shared memory
+//       - 1x1 convs: A is the [M, Cin] activation matrix (2D tiled map)
+//       - 3x3 convs: A tiles come from the NHWC tensor through an im2col-mode
+//         tensor map; the 9 filter taps are 9 K-slices addressed by (offW, offH),
+//         'same' zero padding falls out of the map's bounding box + OOB fill
+//   * tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16) issued by one thread,
+//     fp32 accumulators double-buffered in TMEM
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+//     warps 4-7 epilogue (tcgen05.ld -> bias/activation/residual -> global)
+//   * persistent over output tiles (grid = min(tiles, SMs))
+//
+// Reference ops covered: the pointwise half of tf.layers.separable_conv2d and
+// tf.layers.conv2d with kernel 1 or 3 (src/net_factory.py:5,15,25), with the
+// folded batch-norm / bias / ReLU / ELU / tf.add epilogues of :9-11,18-19,29,37.
+#include <stdlib.h>
+#include <string.h>
+
+#include "lwop_kernels.cuh"
+
+namespace lwop {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+
+struct GemmParams {
+    const float *bias;              // [Cout_pad]
+    const __nv_bfloat16 *residual;  // [M][ldr] or nullptr
+    void *out;                      // bf16 or fp32, [M][ldo], column offset out_col0
+    float *out2;                    // optional fp32 copy [M][Cout] (narrow heads)
+    long long M;
+    int H, W;                       // spatial size (im2col decomposition of m)
+    int Cout, Cout_pad;
+    int k_blocks_per_tap, taps, dil;
+    int ldo, out_col0, ldr;
+    int out_is_f32, act;
+    int num_m_tiles, num_n_tiles;
+};
+
+template <int BLOCK_N, int KSWZ, int STAGES>
+struct SmemLayout {
+    static constexpr int kABytes = kBlockM * KSWZ;
+    static constexpr int kBBytes = BLOCK_N * KSWZ;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kBiasOffset = kBarOffset + 256;
+    static constexpr int kTotal = kBiasOffset + 512 * 4 + 1024;   // + alignment slack
+};
+
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+    using L = SmemLayout<BLOCK_N, KSWZ, STAGES>;
+    constexpr int BLOCK_K = KSWZ / 2;                 // bf16 elements per swizzle row
+    constexpr int kMmasPerBlock = BLOCK_K / 16;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                            ~static_cast<uintptr_t>(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int k_blocks = p.taps * p.k_blocks_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);            // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+    for (int i = threadIdx.x; i < p.Cout_pad; i += kNumThreads) bias_s[i] = p.bias[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+                const long long m0 = (long long)m_tile * kBlockM;
+                int pn = 0, ph = 0, pw = 0;
+                if (IM2COL) {
+                    const int hw = p.H * p.W;
+                    pn = (int)(m0 / hw);
+                    const int rem = (int)(m0 - (long long)pn * hw);
+                    ph = rem / p.W;
+                    pw = rem - ph * p.W;
+                }
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * L::kStageBytes;
+                    unsigned char *sb = sa + L::kABytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                    const int tap = kb / p.k_blocks_per_tap;
+                    const int c0 = (kb - tap * p.k_blocks_per_tap) * BLOCK_K;
+                    if (IM2COL) {
+                        const int r = tap / 3, s = tap - r * 3;
+                        tma_load_im2col_4d(sa, &map_a, &full_bar[stage], c0, pw - p.dil, ph - p.dil, pn,
+                                           (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+                    } else {
+                        tma_load_2d(sa, &map_a, &full_bar[stage], c0, (int)m0);
+                    }
+                    tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+                    const uint64_t da = make_kmajor_desc<KSWZ>(sa);
+                    const uint64_t db = make_kmajor_desc<KSWZ>(sb);
+#pragma unroll
+                    for (int k = 0; k < kMmasPerBlock; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+                        umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpilogueWarp0) {
+        // ===================== epilogue =====================
+        const int q = warp - kEpilogueWarp0;                 // TMEM lane quarter == warp % 4
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool narrow = (p.Cout != p.Cout_pad) || p.out_is_f32 || (p.out_col0 & 7) || (p.ldo & 7);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+            const long long m = (long long)m_tile * kBlockM + q * 32 + lane;
+            const int n0 = n_tile * BLOCK_N;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const bool row_ok = m < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 16) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)c, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_s[n0 + c + j], p.act);
+                if (row_ok) {
+                    if (p.residual) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + n0 + c);
+                        const uint4 r0 = rp[0], r1 = rp[1];
+                        v[0] += bf16_lo(r0.x); v[1] += bf16_hi(r0.x); v[2] += bf16_lo(r0.y); v[3] += bf16_hi(r0.y);
+                        v[4] += bf16_lo(r0.z); v[5] += bf16_hi(r0.z); v[6] += bf16_lo(r0.w); v[7] += bf16_hi(r0.w);
+                        v[8] += bf16_lo(r1.x); v[9] += bf16_hi(r1.x); v[10] += bf16_lo(r1.y); v[11] += bf16_hi(r1.y);
+                        v[12] += bf16_lo(r1.z); v[13] += bf16_hi(r1.z); v[14] += bf16_lo(r1.w); v[15] += bf16_hi(r1.w);
+                    }
+                    if (!narrow) {
+                        uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + m * p.ldo +
+                                                              p.out_col0 + n0 + c);
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+                        o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+                        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+                        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                        op[0] = o0;
+                        op[1] = o1;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c + j;
+                            if (n < p.Cout) {
+                                if (p.out_is_f32)
+                                    reinterpret_cast<float *>(p.out)[m * p.ldo + p.out_col0 + n] = v[j];
+                                else
+                                    reinterpret_cast<__nv_bfloat16 *>(p.out)[m * p.ldo + p.out_col0 + n] =
+                                        __float2bfloat16_rn(v[j]);
+                                if (p.out2) p.out2[m * p.Cout + n] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_num_sms = 0;
+
+}  // namespace
+
+// libcuda is resolved at run time through the runtime's driver entry points so
+// that the shared library still loads (and exports its symbols) on a machine
+// without a GPU driver.
+bool gemm_driver_ready(char *err, size_t errlen) {
+    if (g_encode_tiled && g_encode_im2col) return true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return false;
+    }
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(err, errlen, "cuTensorMapEncodeIm2col not available: %s", cudaGetErrorString(e));
+        return false;
+    }
+    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    return true;
+}
+
+struct GemmPlan {
+    CUtensorMap map_a, map_b;
+    GemmParams p;
+    int block_n, kswz, im2col, stages;
+    int grid;
+    size_t smem;
+};
+
+namespace {
+
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
+cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    auto kfn = gemm_conv_kernel<BLOCK_N, KSWZ, IM2COL, STAGES>;
+    constexpr size_t smem = SmemLayout<BLOCK_N, KSWZ, STAGES>::kTotal;
+    // per-device attribute; cheap enough to set on every launch (and outside graph replay)
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    GemmParams p = pl->p;
+    if (out_override) p.out = out_override;
+    if (out2_override) p.out2 = out2_override;
+    kfn<<<pl->grid, kNumThreads, smem, s>>>(pl->map_a, pl->map_b, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    if (pl->im2col) {
+        if (pl->block_n == 128 && pl->kswz == 128) return launch_t<128, 128, true, 6>(pl, s, out_override, out2_override);
+        return cudaErrorInvalidValue;
+    }
+    if (pl->kswz == 64) {
+        if (pl->block_n == 64) return launch_t<64, 64, false, 8>(pl, s, out_override, out2_override);
+        return cudaErrorInvalidValue;
+    }
+    switch (pl->block_n) {
+        case 16: return launch_t<16, 128, false, 8>(pl, s, out_override, out2_override);
+        case 32: return launch_t<32, 128, false, 8>(pl, s, out_override, out2_override);
+        case 64: return launch_t<64, 128, false, 8>(pl, s, out_override, out2_override);
+        case 128: return launch_t<128, 128, false, 6>(pl, s, out_override, out2_override);
+        case 256: return launch_t<256, 128, false, 4>(pl, s, out_override, out2_override);
+    }
+    return cudaErrorInvalidValue;
+}
+
+GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
+    if (!gemm_driver_ready(err, errlen)) return nullptr;
+    if (d.ksize != 1 && d.ksize != 3) {
+        snprintf(err, errlen, "gemm conv: kernel size %d unsupported", d.ksize);
+        return nullptr;
+    }
+    const int kswz = (d.Cin_pad % 64 == 0) ? 128 : 64;
+    const int block_k = kswz / 2;
+    if (d.Cin_pad % block_k != 0 || d.Cin_pad < 32) {
+        snprintf(err, errlen, "gemm conv: Cin_pad=%d must be a multiple of 32", d.Cin_pad);
+        return nullptr;
+    }
+    int block_n;
+    if (d.Cout_pad % 256 == 0) block_n = 256;
+    else if (d.Cout_pad % 128 == 0) block_n = 128;
+    else if (d.Cout_pad == 64 || d.Cout_pad == 32 || d.Cout_pad == 16) block_n = d.Cout_pad;
+    else {
+        snprintf(err, errlen, "gemm conv: Cout_pad=%d unsupported", d.Cout_pad);
+        return nullptr;
+    }
+    const bool im2col = d.ksize == 3;
+    if (im2col && d.Cout_pad % 128 == 0) block_n = 128;
+    if (im2col && !(block_n == 128 && kswz == 128)) {
+        snprintf(err, errlen, "gemm conv 3x3: only Cout_pad %% 128 == 0 and Cin %% 64 == 0 supported");
+        return nullptr;
+    }
+    if (kswz == 64 && block_n != 64) {
+        snprintf(err, errlen, "gemm conv: Cin_pad=32 only supported with Cout_pad=64");
+        return nullptr;
+    }
+    GemmPlan *pl = (GemmPlan *)calloc(1, sizeof(GemmPlan));
+    const long long M = (long long)d.B * d.H * d.W;
+    const int taps = d.ksize * d.ksize;
+    pl->block_n = block_n;
+    pl->kswz = kswz;
+    pl->im2col = im2col;
+    GemmParams &p = pl->p;
+    p.bias = d.bias;
+    p.residual = (const __nv_bfloat16 *)d.residual;
+    p.out = d.out;
+    p.out2 = d.out2;
+    p.M = M;
+    p.H = d.H;
+    p.W = d.W;
+    p.Cout = d.Cout;
+    p.Cout_pad = d.Cout_pad;
+    p.k_blocks_per_tap = d.Cin_pad / block_k;
+    p.taps = taps;
+    p.dil = d.dil;
+    p.ldo = d.ldo;
+    p.out_col0 = d.out_col0;
+    p.ldr = d.ldr;
+    p.out_is_f32 = d.out_dtype == LWOP_DT_F32;
+    p.act = d.act;
+    p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+    p.num_n_tiles = d.Cout_pad / block_n;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    pl->grid = tiles < g_num_sms ? tiles : g_num_sms;
+
+    const CUtensorMapSwizzle swz = kswz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r;
+    if (!im2col) {
+        cuuint64_t dims[2] = {(cuuint64_t)d.Cin_pad, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)d.lda * 2};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)kBlockM};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encode_tiled(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.in), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin_pad, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.W * d.lda * 2,
+                                 (cuuint64_t)d.H * d.W * d.lda * 2};
+        int lower[2] = {-d.dil, -d.dil};                  // {W, H}: filter window may start `pad` left/above
+        int upper[2] = {-d.dil, -d.dil};                  // pad - (k-1)*dil = dil - 2*dil
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = g_encode_im2col(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.in), dims, strides,
+                            lower, upper, (cuuint32_t)block_k, (cuuint32_t)kBlockM, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r == CUDA_SUCCESS && im2col) {
+        // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers up to
+        // 13.1 mis-encode im2col maps of tensors smaller than 128 KiB; clear bit 21 of word 1.
+        int drv = 0;
+        cudaDriverGetVersion(&drv);
+        const unsigned long long bytes = (unsigned long long)d.B * d.H * d.W * d.lda * 2ull;
+        if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t *>(&pl->map_a)[1] &= ~(1ull << 21);
+    }
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "tensor map (A, %s) encode failed: CUresult %d", im2col ? "im2col" : "tiled", (int)r);
+        free(pl);
+        return nullptr;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)taps * d.Cin_pad, (cuuint64_t)d.Cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)taps * d.Cin_pad * 2};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encode_tiled(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.w_packed), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(err, errlen, "tensor map (B) encode failed: CUresult %d", (int)r);
+            free(pl);
+            return nullptr;
+        }
+    }
+    return pl;
+}
+
+void gemm_plan_destroy(GemmPlan *p) { free(p); }
+
+}  // namespace lwop

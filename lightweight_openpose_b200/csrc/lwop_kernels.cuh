@@ -1,0 +1,84 @@
+// Launch prototypes shared between the kernel translation units and the executor.
+#pragma once
+#include "lwop_common.cuh"
+
+namespace lwop {
+
+struct ConvArgs {
+    const void *in;        // NHWC
+    int in_dtype;          // LWOP_DT_*
+    const float *w;        // [Cout][k*k][Cin] fp32
+    const float *bias;     // [Cout] or nullptr
+    const void *residual;  // same dtype/shape as out, added after the activation, or nullptr
+    void *out;
+    int out_dtype;
+    int B, H, W, Cin, Cout, ksize, stride, dil, act;
+    int ldi = 0;           // input pixel pitch in elements (0 = Cin)
+    int ldo = 0;           // output row pitch in elements (0 = Cout)
+    int out_col0 = 0;      // first output column
+    int ldr = 0;           // residual row pitch (0 = Cout)
+};
+
+struct DwArgs {
+    const void *in;
+    void *out;
+    int dtype;
+    const float *w;        // [9][C] fp32
+    int B, H, W, C, stride, dil;
+};
+
+// lwop_direct.cu
+cudaError_t launch_conv_direct(const ConvArgs &a, cudaStream_t s);
+cudaError_t launch_depthwise_simple(const DwArgs &a, cudaStream_t s);
+cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s);
+cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, const float *w, const float *bias, void *out, int B,
+                              int H, int W, cudaStream_t s);
+cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStream_t s);
+cudaError_t launch_pack_bf16(const float *src, void *dst, long long rows, int cols, int cols_padded,
+                             cudaStream_t s);
+
+// lwop_gemm.cu -- tcgen05 implicit-GEMM conv (1x1 and 3x3, stride 1)
+struct GemmPlan;   // opaque: tensor maps + launch geometry for one layer at one (B, H, W)
+
+struct GemmConvDesc {
+    const void *in;            // bf16 NHWC [B,H,W,Cin_pad]   (Cin_pad multiple of 32)
+    const void *w_packed;      // bf16 [Cout_pad][taps][Cin_pad]
+    const float *bias;         // fp32 [Cout_pad]
+    const void *residual;      // bf16 [M][ldr] or nullptr
+    void *out;                 // bf16 or fp32 [M][ldo] written at column offset out_col0
+    float *out2;               // optional fp32 copy [M][Cout] (narrow heads only) or nullptr
+    int out_dtype;
+    int lda;                   // input pixel pitch in elements
+    int B, H, W;
+    int Cin_pad, Cout, Cout_pad, ksize, dil, act;
+    int ldo, out_col0;         // output row pitch (elements) and first column
+    int ldr;                   // residual row pitch (elements)
+};
+
+GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen);
+void gemm_plan_destroy(GemmPlan *p);
+// out_override/out2_override (may be nullptr) replace the plan's output pointers for this launch.
+cudaError_t gemm_plan_launch(const GemmPlan *p, cudaStream_t s, void *out_override = nullptr,
+                             float *out2_override = nullptr);
+bool gemm_driver_ready(char *err, size_t errlen);
+
+// lwop_decode.cu
+struct DecodeArgs {
+    const float *heat;   // [B,h,w,14]
+    const float *paf;    // [B,h,w,26]
+    int B, h, w, H, W;
+    float thre1;
+    double thre2;
+    lwop_decode_tables t;
+    // scratch owned by the handle
+    float *peaks;        // [B][14][LWOP_MAX_PEAKS][4]  (x, y, score, unused) in kept order
+    int *peak_counts;    // [B][16]
+};
+cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launches);
+size_t decode_scratch_peaks_bytes(int B);
+// compaction of the fixed-capacity tables: offsets[b][4] = exclusive prefix of (joints, persons, conns, 0)
+cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,
+                               double *limbs_packed, double *persons_packed, float *keypoints_packed,
+                               cudaStream_t s, long long *launches);
+
+}  // namespace lwop

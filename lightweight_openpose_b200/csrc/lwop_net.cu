@@ -1,0 +1,840 @@
+// Handle, weight store, whole-network executor and the extern "C" entry points
+// declared in include/lwop.h.
+//
+// The layer table below restates the graph of the reference
+// src/lightweight_openpose.py:8-48 (built from src/net_factory.py:4-37) in
+// creation order; lightweight_openpose_b200/graph.py holds the same table on
+// the Python side (variable names, BN folding) and the packed-weight blob must
+// match lwop_weights_num_floats() exactly.
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lwop_kernels.cuh"
+
+using namespace lwop;
+
+namespace {
+
+enum LayerKind { L_CONV = 0, L_SEP = 1 };
+
+struct LayerSpec {
+    int kind, cin, cout, k, stride, dil, act;
+};
+
+// clang-format off
+const LayerSpec kLayers[] = {
+    // BackBone (lightweight_openpose.py:9-21)
+    {L_CONV,   3,  32, 3, 2, 1, LWOP_ACT_RELU},
+    {L_SEP,   32,  64, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,   64, 128, 1, 2, 1, LWOP_ACT_RELU},
+    {L_SEP,  128, 128, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  128, 256, 1, 2, 1, LWOP_ACT_RELU},
+    {L_SEP,  256, 256, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  256, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  512, 512, 1, 1, 2, LWOP_ACT_RELU},
+    {L_SEP,  512, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  512, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  512, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  512, 512, 1, 1, 1, LWOP_ACT_RELU},
+    // Cpm (:22-27)
+    {L_CONV, 512, 128, 1, 1, 1, LWOP_ACT_RELU},
+    {L_SEP,  128, 128, 1, 1, 1, LWOP_ACT_ELU},
+    {L_SEP,  128, 128, 1, 1, 1, LWOP_ACT_ELU},
+    {L_SEP,  128, 128, 1, 1, 1, LWOP_ACT_ELU},
+    {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU},
+    // InitialStage (:28-36)
+    {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 128, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 512,  14, 1, 1, 1, LWOP_ACT_NONE},
+    {L_CONV, 128, 512, 1, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 512,  26, 1, 1, 1, LWOP_ACT_NONE},
+    // RefinementStage (:37-46), 5 x RefinementStageBlock (net_factory.py:33-37)
+    {L_CONV,  40, 128, 1, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 2, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 2, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 2, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 2, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 1, LWOP_ACT_RELU}, {L_CONV, 128, 128, 3, 1, 2, LWOP_ACT_RELU},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 128,  14, 1, 1, 1, LWOP_ACT_NONE},
+    {L_CONV, 128, 128, 1, 1, 1, LWOP_ACT_RELU},
+    {L_CONV, 128,  26, 1, 1, 1, LWOP_ACT_NONE},
+};
+// clang-format on
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+static_assert(kNumLayers == 43, "layer table out of sync with graph.py");
+
+enum BufId { B_IN = 0, B_A, B_B, B_D, B_ALIGN, B_T0, B_T1, B_CAT, B_INIT, B_HEAT, B_PAF, B_H1, B_P1, NUM_BUF };
+
+struct Step {
+    int layer;
+    bool is_dw;        // depthwise half of a separable layer
+    int in, out, res;  // BufId (res = -1: none)
+    int H, W;          // input spatial size
+    int cin_pad;       // input channels / pitch
+    int ldo, col0;     // output pitch / first column
+    int out_f32;       // output is a caller-owned fp32 map (final heads)
+    int out2;          // BufId of optional fp32 copy (stage-1 heads), -1 none
+};
+
+int pad_cout(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : (c <= 64 ? 64 : ((c + 127) / 128) * 128)); }
+int pad_cin(int c) { return c == 40 ? 64 : c; }
+
+struct PlanSet {
+    std::vector<GemmPlan *> plans;   // per step (nullptr for non-GEMM steps)
+};
+
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    const void *in = nullptr;
+    void *heat = nullptr, *paf = nullptr, *h1 = nullptr, *p1 = nullptr;
+    int in_u8 = 0;
+};
+
+}  // namespace
+
+struct lwop_handle {
+    int device = 0, max_batch = 0, H = 0, W = 0;
+    unsigned flags = 0;
+    int h2 = 0, w2 = 0, h4 = 0, w4 = 0, h8 = 0, w8 = 0;
+    std::string err;
+    long long launches = 0;
+
+    // weights
+    bool has_weights = false;
+    float *blob = nullptr;                       // fp32 folded weights, blob layout
+    size_t off_dw[kNumLayers] = {}, off_w[kNumLayers] = {}, off_b[kNumLayers] = {};
+    void *w_bf16[kNumLayers] = {};               // [Cout_pad][taps][Cin_pad] bf16
+    float *b_pad[kNumLayers] = {};               // [Cout_pad] fp32
+    float *w_f32pad[kNumLayers] = {};            // fp32 weights with padded Cin (only layer 24: 40 -> 64)
+
+    // program + arenas
+    std::vector<Step> steps;
+    size_t buf_elems[NUM_BUF] = {};              // elements per image
+    void *arena_bf16[NUM_BUF] = {};
+    void *arena_f32[NUM_BUF] = {};
+    std::map<int, PlanSet> plan_sets;            // by batch
+    std::map<long long, GraphEntry> graphs;      // by batch * 8 + mode
+
+    // decode scratch
+    float *peaks = nullptr;
+    int *peak_counts = nullptr;
+    int *pack_offsets = nullptr;
+    double *pk_joints = nullptr, *pk_limbs = nullptr, *pk_persons = nullptr;
+    float *pk_keypoints = nullptr;
+    size_t pk_joints_cap = 0, pk_limbs_cap = 0, pk_persons_cap = 0;
+    int *h_offsets = nullptr;                    // pinned
+    // infer_host staging
+    void *stage_in = nullptr;
+    size_t stage_in_bytes = 0;
+    float *stage_heat = nullptr, *stage_paf = nullptr;
+    lwop_decode_tables own_tables = {};
+    int own_tables_batch = 0;
+};
+
+namespace {
+
+std::string g_last_error;
+std::mutex g_err_mutex;
+
+int fail(lwop_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_OK(h, expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(h, LWOP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+size_t blob_floats() {
+    size_t n = 0;
+    for (int i = 0; i < kNumLayers; ++i) {
+        const LayerSpec &l = kLayers[i];
+        if (l.kind == L_SEP) n += 9 * (size_t)l.cin;
+        n += (size_t)l.cout * l.k * l.k * l.cin + l.cout;
+    }
+    return n;
+}
+
+void build_program(lwop_handle *h) {
+    auto &S = h->steps;
+    S.clear();
+    for (int i = 0; i < NUM_BUF; ++i) h->buf_elems[i] = 0;
+    auto need = [&](int buf, size_t elems) {
+        if (elems > h->buf_elems[buf]) h->buf_elems[buf] = elems;
+    };
+    int H = h->H, W = h->W;
+    auto add = [&](int layer, bool is_dw, int in, int out, int res, int inH, int inW, int cin_pad, int ldo, int col0,
+                   int out_f32 = 0, int out2 = -1) {
+        Step s{layer, is_dw, in, out, res, inH, inW, cin_pad, ldo, col0, out_f32, out2};
+        S.push_back(s);
+    };
+    // layer 0: conv1
+    add(0, false, B_IN, B_A, -1, H, W, 3, 32, 0);
+    H = h->h2; W = h->w2;
+    need(B_A, (size_t)H * W * 32);
+    int cur = B_A;
+    for (int li = 1; li <= 11; ++li) {
+        const LayerSpec &l = kLayers[li];
+        const int oH = (H + l.stride - 1) / l.stride, oW = (W + l.stride - 1) / l.stride;
+        add(li, true, cur, B_D, -1, H, W, l.cin, l.cin, 0);
+        need(B_D, (size_t)oH * oW * l.cin);
+        const int nxt = cur == B_A ? B_B : B_A;
+        add(li, false, B_D, nxt, -1, oH, oW, l.cin, l.cout, 0);
+        need(nxt, (size_t)oH * oW * l.cout);
+        cur = nxt;
+        H = oH; W = oW;
+    }
+    const size_t px = (size_t)H * W;      // stride-8 pixels
+    for (int b : {B_ALIGN, B_T0, B_T1, B_INIT}) need(b, px * 128);
+    need(B_CAT, px * 64);
+    need(B_A, px * 512);
+    need(B_B, px * 512);
+    need(B_D, px * 128);
+    // Cpm
+    add(12, false, cur, B_ALIGN, -1, H, W, 512, 128, 0);
+    add(13, true, B_ALIGN, B_D, -1, H, W, 128, 128, 0);
+    add(13, false, B_D, B_T0, -1, H, W, 128, 128, 0);
+    add(14, true, B_T0, B_D, -1, H, W, 128, 128, 0);
+    add(14, false, B_D, B_T1, -1, H, W, 128, 128, 0);
+    add(15, true, B_T1, B_D, -1, H, W, 128, 128, 0);
+    add(15, false, B_D, B_T0, B_ALIGN, H, W, 128, 128, 0);          // tf.add(net_align, net_truck) (:27)
+    add(16, false, B_T0, B_T1, -1, H, W, 128, 128, 0);
+    // InitialStage
+    add(17, false, B_T1, B_T0, -1, H, W, 128, 128, 0);
+    add(18, false, B_T0, B_T1, -1, H, W, 128, 128, 0);
+    add(19, false, B_T1, B_T0, -1, H, W, 128, 128, 0);
+    add(20, false, B_T0, B_A, -1, H, W, 128, 512, 0);
+    add(21, false, B_A, B_CAT, -1, H, W, 512, 64, 0, 0, B_H1);      // heatmaps1 -> concat cols 0..13 (:36)
+    add(22, false, B_T0, B_A, -1, H, W, 128, 512, 0);
+    add(23, false, B_A, B_CAT, -1, H, W, 512, 64, 14, 0, B_P1);     // pafs1 -> concat cols 14..39
+    // RefinementStage
+    int in = B_CAT;
+    for (int b = 0; b < 5; ++b) {
+        const int l0 = 24 + 3 * b;
+        add(l0, false, in, B_INIT, -1, H, W, b == 0 ? 64 : 128, 128, 0);
+        add(l0 + 1, false, B_INIT, B_T1, -1, H, W, 128, 128, 0);
+        add(l0 + 2, false, B_T1, B_T0, B_INIT, H, W, 128, 128, 0);  // tf.add(net_initial, net_truck) (net_factory.py:37)
+        in = B_T0;
+    }
+    add(39, false, B_T0, B_T1, -1, H, W, 128, 128, 0);
+    add(40, false, B_T1, B_HEAT, -1, H, W, 128, 14, 0, 1);
+    add(41, false, B_T0, B_T1, -1, H, W, 128, 128, 0);
+    add(42, false, B_T1, B_PAF, -1, H, W, 128, 26, 0, 1);
+}
+
+int ensure_arena(lwop_handle *h, int mode) {
+    void **arena = mode == LWOP_MODE_FP32_CHECK ? h->arena_f32 : h->arena_bf16;
+    const size_t esz = mode == LWOP_MODE_FP32_CHECK ? 4 : 2;
+    for (int b = B_A; b <= B_INIT; ++b) {
+        if (arena[b] || h->buf_elems[b] == 0) continue;
+        const size_t bytes = h->buf_elems[b] * esz * (size_t)h->max_batch + 4096;   // slack: TMA tail tiles never fault
+        CU_OK(h, cudaMalloc(&arena[b], bytes));
+        CU_OK(h, cudaMemset(arena[b], 0, bytes));
+    }
+    return LWOP_OK;
+}
+
+void destroy_plans(lwop_handle *h) {
+    for (auto &kv : h->plan_sets)
+        for (GemmPlan *p : kv.second.plans)
+            if (p) gemm_plan_destroy(p);
+    h->plan_sets.clear();
+    for (auto &kv : h->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+}
+
+bool step_uses_gemm(const Step &s) { return !s.is_dw && s.layer != 0; }
+
+int get_plans(lwop_handle *h, int batch, PlanSet **out) {
+    auto it = h->plan_sets.find(batch);
+    if (it != h->plan_sets.end()) {
+        *out = &it->second;
+        return LWOP_OK;
+    }
+    PlanSet ps;
+    ps.plans.assign(h->steps.size(), nullptr);
+    char err[256];
+    for (size_t i = 0; i < h->steps.size(); ++i) {
+        const Step &s = h->steps[i];
+        if (!step_uses_gemm(s)) continue;
+        const LayerSpec &l = kLayers[s.layer];
+        GemmConvDesc d{};
+        d.in = h->arena_bf16[s.in];
+        d.w_packed = h->w_bf16[s.layer];
+        d.bias = h->b_pad[s.layer];
+        d.residual = s.res >= 0 ? h->arena_bf16[s.res] : nullptr;
+        d.out = s.out_f32 ? nullptr : h->arena_bf16[s.out];
+        d.out2 = nullptr;
+        d.out_dtype = s.out_f32 ? LWOP_DT_F32 : LWOP_DT_BF16;
+        d.lda = s.cin_pad;
+        d.B = batch;
+        d.H = s.H;
+        d.W = s.W;
+        d.Cin_pad = s.cin_pad;
+        d.Cout = l.cout;
+        d.Cout_pad = pad_cout(l.cout);
+        d.ksize = l.k;
+        d.dil = l.dil;
+        d.act = l.act;
+        d.ldo = s.ldo;
+        d.out_col0 = s.col0;
+        d.ldr = 128;
+        ps.plans[i] = gemm_plan_create(d, err, sizeof(err));
+        if (!ps.plans[i]) {
+            for (GemmPlan *p : ps.plans)
+                if (p) gemm_plan_destroy(p);
+            return fail(h, LWOP_ERR_UNSUPPORTED, std::string("layer ") + std::to_string(s.layer) + ": " + err);
+        }
+    }
+    auto res = h->plan_sets.emplace(batch, std::move(ps));
+    *out = &res.first->second;
+    return LWOP_OK;
+}
+
+struct FwdIO {
+    const void *in;
+    int in_u8;
+    float *heat, *paf, *h1, *p1;
+};
+
+// Issue every kernel of one forward pass on `s`.
+int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream_t s) {
+    const bool f32 = mode == LWOP_MODE_FP32_CHECK;
+    void **arena = f32 ? h->arena_f32 : h->arena_bf16;
+    const int dt = f32 ? LWOP_DT_F32 : LWOP_DT_BF16;
+    PlanSet *ps = nullptr;
+    if (mode == LWOP_MODE_BF16) {
+        int rc = get_plans(h, batch, &ps);
+        if (rc != LWOP_OK) return rc;
+    }
+    const float *in_f32 = (const float *)io.in;
+    if (io.in_u8 && mode != LWOP_MODE_BF16 && mode != LWOP_MODE_BF16_DIRECT) {
+        // fp32 check path: normalise into a staging buffer first
+        const long long n = (long long)batch * h->H * h->W * 3;
+        if (!h->arena_f32[B_IN]) {
+            CU_OK(h, cudaMalloc(&h->arena_f32[B_IN], (size_t)h->max_batch * h->H * h->W * 3 * 4));
+        }
+        CU_OK(h, launch_u8_to_f32((const uint8_t *)io.in, (float *)h->arena_f32[B_IN], n, s));
+        h->launches++;
+        in_f32 = (const float *)h->arena_f32[B_IN];
+    }
+    for (size_t i = 0; i < h->steps.size(); ++i) {
+        const Step &st = h->steps[i];
+        const LayerSpec &l = kLayers[st.layer];
+        void *out = st.out == B_HEAT ? (void *)io.heat : st.out == B_PAF ? (void *)io.paf : arena[st.out];
+        const void *in = st.in == B_IN ? (const void *)in_f32 : arena[st.in];
+        float *out2 = st.out2 == B_H1 ? io.h1 : st.out2 == B_P1 ? io.p1 : nullptr;
+        if (st.layer == 0) {
+            if (!f32) {
+                CU_OK(h, launch_conv1_bf16(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, h->blob + h->off_w[0],
+                                           h->blob + h->off_b[0], out, batch, st.H, st.W, s));
+            } else {
+                ConvArgs a{};
+                a.in = in_f32; a.in_dtype = LWOP_DT_F32; a.w = h->blob + h->off_w[0]; a.bias = h->blob + h->off_b[0];
+                a.out = out; a.out_dtype = LWOP_DT_F32;
+                a.B = batch; a.H = st.H; a.W = st.W; a.Cin = 3; a.Cout = 32; a.ksize = 3; a.stride = 2; a.dil = 1;
+                a.act = LWOP_ACT_RELU;
+                CU_OK(h, launch_conv_direct(a, s));
+            }
+            h->launches++;
+            continue;
+        }
+        if (st.is_dw) {
+            DwArgs a{};
+            a.in = in; a.out = out; a.dtype = dt; a.w = h->blob + h->off_dw[st.layer];
+            a.B = batch; a.H = st.H; a.W = st.W; a.C = l.cin; a.stride = l.stride; a.dil = l.dil;
+            if (f32) CU_OK(h, launch_depthwise_simple(a, s));
+            else CU_OK(h, launch_depthwise_bf16(a, s));
+            h->launches++;
+            continue;
+        }
+        if (mode == LWOP_MODE_BF16) {
+            CU_OK(h, gemm_plan_launch(ps->plans[i], s, st.out_f32 ? out : nullptr, out2));
+            h->launches++;
+            continue;
+        }
+        // direct (CUDA-core) conv: fp32 check path or bf16-storage debugging path
+        ConvArgs a{};
+        a.in = in; a.in_dtype = dt;
+        a.w = (st.cin_pad != l.cin && h->w_f32pad[st.layer]) ? h->w_f32pad[st.layer] : h->blob + h->off_w[st.layer];
+        a.bias = h->blob + h->off_b[st.layer];
+        a.residual = st.res >= 0 ? arena[st.res] : nullptr;
+        a.out = out; a.out_dtype = st.out_f32 ? LWOP_DT_F32 : dt;
+        a.B = batch; a.H = st.H; a.W = st.W; a.Cin = st.cin_pad; a.Cout = l.cout; a.ksize = l.k; a.stride = 1;
+        a.dil = l.dil; a.act = l.act; a.ldi = st.cin_pad; a.ldo = st.ldo; a.out_col0 = st.col0; a.ldr = 128;
+        CU_OK(h, launch_conv_direct(a, s));
+        h->launches++;
+        if (out2) {   // stage-1 heads also wanted as fp32 maps
+            a.out = out2; a.out_dtype = LWOP_DT_F32; a.ldo = l.cout; a.out_col0 = 0;
+            CU_OK(h, launch_conv_direct(a, s));
+            h->launches++;
+        }
+    }
+    return LWOP_OK;
+}
+
+int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStream_t s) {
+    if (!h) return fail(nullptr, LWOP_ERR_INVALID, "null handle");
+    if (!h->has_weights) return fail(h, LWOP_ERR_NO_WEIGHTS, "lwop_forward before lwop_load_weights");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    if (mode != LWOP_MODE_BF16 && mode != LWOP_MODE_FP32_CHECK && mode != LWOP_MODE_BF16_DIRECT)
+        return fail(h, LWOP_ERR_INVALID, "unknown mode");
+    if (!io.in || !io.heat || !io.paf) return fail(h, LWOP_ERR_INVALID, "null tensor pointer");
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_arena(h, mode);
+    if (rc != LWOP_OK) return rc;
+    const bool use_graph = !(h->flags & LWOP_FLAG_NO_GRAPH) && mode == LWOP_MODE_BF16;
+    if (!use_graph) return run_forward(h, batch, mode, io, s);
+
+    const long long key = (long long)batch * 8 + mode;
+    GraphEntry &g = h->graphs[key];
+    const bool same = g.exec && g.in == io.in && g.heat == io.heat && g.paf == io.paf && g.h1 == io.h1 &&
+                      g.p1 == io.p1 && g.in_u8 == io.in_u8;
+    if (!same) {
+        if (g.exec) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        // One eager pass first: creates the plans (tensor-map encoding calls the driver), sets the
+        // per-kernel shared-memory attributes and surfaces launch errors outside of stream capture.
+        rc = run_forward(h, batch, mode, io, s);
+        if (rc != LWOP_OK) return rc;
+        CU_OK(h, cudaStreamSynchronize(s));
+        cudaStream_t cs;
+        CU_OK(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            const long long before = h->launches;
+            rc = run_forward(h, batch, mode, io, cs);
+            h->launches = before;                      // counted again at each replay
+            e = cudaStreamEndCapture(cs, &graph);
+        }
+        if (e != cudaSuccess || rc != LWOP_OK || !graph) {
+            cudaStreamDestroy(cs);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != LWOP_OK) return rc;
+            return fail(h, LWOP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        g.in = io.in; g.heat = io.heat; g.paf = io.paf; g.h1 = io.h1; g.p1 = io.p1; g.in_u8 = io.in_u8;
+    }
+    CU_OK(h, cudaGraphLaunch(g.exec, s));
+    h->launches += (long long)h->steps.size();
+    return LWOP_OK;
+}
+
+int ensure_decode_scratch(lwop_handle *h) {
+    if (h->peaks) return LWOP_OK;
+    CU_OK(h, cudaMalloc(&h->peaks, decode_scratch_peaks_bytes(h->max_batch)));
+    CU_OK(h, cudaMalloc(&h->peak_counts, (size_t)h->max_batch * 16 * sizeof(int)));
+    CU_OK(h, cudaMalloc(&h->pack_offsets, ((size_t)h->max_batch + 1) * 4 * sizeof(int)));
+    CU_OK(h, cudaMallocHost(&h->h_offsets, ((size_t)h->max_batch + 1) * 4 * sizeof(int)));
+    return LWOP_OK;
+}
+
+int ensure_pack_buffers(lwop_handle *h, size_t joints, size_t limbs, size_t persons) {
+    if (joints > h->pk_joints_cap) {
+        if (h->pk_joints) cudaFree(h->pk_joints);
+        h->pk_joints_cap = joints + joints / 2 + 1024;
+        CU_OK(h, cudaMalloc(&h->pk_joints, h->pk_joints_cap * 6 * sizeof(double)));
+    }
+    if (limbs > h->pk_limbs_cap) {
+        if (h->pk_limbs) cudaFree(h->pk_limbs);
+        h->pk_limbs_cap = limbs + limbs / 2 + 1024;
+        CU_OK(h, cudaMalloc(&h->pk_limbs, h->pk_limbs_cap * 5 * sizeof(double)));
+    }
+    if (persons > h->pk_persons_cap) {
+        if (h->pk_persons) cudaFree(h->pk_persons);
+        if (h->pk_keypoints) cudaFree(h->pk_keypoints);
+        h->pk_persons_cap = persons + persons / 2 + 256;
+        CU_OK(h, cudaMalloc(&h->pk_persons, h->pk_persons_cap * 16 * sizeof(double)));
+        CU_OK(h, cudaMalloc(&h->pk_keypoints, h->pk_persons_cap * 42 * sizeof(float)));
+    }
+    return LWOP_OK;
+}
+
+int ensure_own_tables(lwop_handle *h) {
+    if (h->own_tables.counts) return LWOP_OK;
+    const size_t B = h->max_batch;
+    CU_OK(h, cudaMalloc(&h->own_tables.counts, B * LWOP_COUNTS * sizeof(int32_t)));
+    CU_OK(h, cudaMalloc(&h->own_tables.joints, B * LWOP_MAX_JOINTS * 6 * sizeof(double)));
+    CU_OK(h, cudaMalloc(&h->own_tables.limbs, B * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 5 * sizeof(double)));
+    CU_OK(h, cudaMalloc(&h->own_tables.persons, B * LWOP_MAX_PERSONS * 16 * sizeof(double)));
+    CU_OK(h, cudaMalloc(&h->own_tables.keypoints, B * LWOP_MAX_PERSONS * 42 * sizeof(float)));
+    return LWOP_OK;
+}
+
+uint32_t g_crc_table[8][256];
+std::once_flag g_crc_once;
+void crc_init() {
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+        g_crc_table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+        for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
+}
+
+}  // namespace
+
+extern "C" {
+
+int lwop_abi_version(void) { return LWOP_ABI_VERSION; }
+
+const char *lwop_error_string(int code) {
+    switch (code) {
+        case LWOP_OK: return "ok";
+        case LWOP_ERR_INVALID: return "invalid argument";
+        case LWOP_ERR_CUDA: return "CUDA failure";
+        case LWOP_ERR_NO_WEIGHTS: return "weights not loaded";
+        case LWOP_ERR_OVERFLOW: return "decode table overflow";
+        case LWOP_ERR_UNSUPPORTED: return "unsupported shape or mode";
+        case LWOP_ERR_NO_DEVICE: return "no usable CUDA device";
+    }
+    return "unknown error";
+}
+
+const char *lwop_last_error(const lwop_handle *h) {
+    if (h) return h->err.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    copy = g_last_error;
+    return copy.c_str();
+}
+
+int lwop_same_out(int in, int stride) { return (in + stride - 1) / stride; }
+
+size_t lwop_weights_num_floats(void) { return blob_floats(); }
+
+int lwop_create(int device, int max_batch, int height, int width, unsigned flags, lwop_handle **out) {
+    if (!out) return fail(nullptr, LWOP_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (max_batch < 1 || height < 16 || width < 16) return fail(nullptr, LWOP_ERR_INVALID, "bad geometry");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, LWOP_ERR_NO_DEVICE, "no CUDA device visible");
+    if (device < 0 || device >= ndev) return fail(nullptr, LWOP_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, LWOP_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, LWOP_ERR_NO_DEVICE,
+                    std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                        "; this library is built for sm_100a only");
+    lwop_handle *h = new lwop_handle();
+    h->device = device;
+    h->max_batch = max_batch;
+    h->H = height;
+    h->W = width;
+    h->flags = flags;
+    h->h2 = (height + 1) / 2; h->w2 = (width + 1) / 2;
+    h->h4 = (h->h2 + 1) / 2; h->w4 = (h->w2 + 1) / 2;
+    h->h8 = (h->h4 + 1) / 2; h->w8 = (h->w4 + 1) / 2;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, LWOP_ERR_CUDA, "cudaSetDevice failed");
+    }
+    build_program(h);
+    *out = h;
+    return LWOP_OK;
+}
+
+int lwop_destroy(lwop_handle *h) {
+    if (!h) return LWOP_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    destroy_plans(h);
+    for (int i = 0; i < NUM_BUF; ++i) {
+        if (h->arena_bf16[i]) cudaFree(h->arena_bf16[i]);
+        if (h->arena_f32[i]) cudaFree(h->arena_f32[i]);
+    }
+    for (int i = 0; i < kNumLayers; ++i) {
+        if (h->w_bf16[i]) cudaFree(h->w_bf16[i]);
+        if (h->b_pad[i]) cudaFree(h->b_pad[i]);
+        if (h->w_f32pad[i]) cudaFree(h->w_f32pad[i]);
+    }
+    if (h->blob) cudaFree(h->blob);
+    if (h->peaks) cudaFree(h->peaks);
+    if (h->peak_counts) cudaFree(h->peak_counts);
+    if (h->pack_offsets) cudaFree(h->pack_offsets);
+    if (h->h_offsets) cudaFreeHost(h->h_offsets);
+    if (h->pk_joints) cudaFree(h->pk_joints);
+    if (h->pk_limbs) cudaFree(h->pk_limbs);
+    if (h->pk_persons) cudaFree(h->pk_persons);
+    if (h->pk_keypoints) cudaFree(h->pk_keypoints);
+    if (h->stage_in) cudaFree(h->stage_in);
+    if (h->stage_heat) cudaFree(h->stage_heat);
+    if (h->stage_paf) cudaFree(h->stage_paf);
+    if (h->own_tables.counts) cudaFree(h->own_tables.counts);
+    if (h->own_tables.joints) cudaFree(h->own_tables.joints);
+    if (h->own_tables.limbs) cudaFree(h->own_tables.limbs);
+    if (h->own_tables.persons) cudaFree(h->own_tables.persons);
+    if (h->own_tables.keypoints) cudaFree(h->own_tables.keypoints);
+    delete h;
+    return LWOP_OK;
+}
+
+int lwop_load_weights(lwop_handle *h, const float *host_blob, size_t num_floats) {
+    if (!h || !host_blob) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (num_floats != blob_floats())
+        return fail(h, LWOP_ERR_INVALID,
+                    "weight blob has " + std::to_string(num_floats) + " floats, expected " +
+                        std::to_string(blob_floats()));
+    CU_OK(h, cudaSetDevice(h->device));
+    destroy_plans(h);
+    if (!h->blob) CU_OK(h, cudaMalloc(&h->blob, num_floats * sizeof(float)));
+    CU_OK(h, cudaMemcpy(h->blob, host_blob, num_floats * sizeof(float), cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int i = 0; i < kNumLayers; ++i) {
+        const LayerSpec &l = kLayers[i];
+        if (l.kind == L_SEP) {
+            h->off_dw[i] = off;
+            off += 9 * (size_t)l.cin;
+        }
+        h->off_w[i] = off;
+        off += (size_t)l.cout * l.k * l.k * l.cin;
+        h->off_b[i] = off;
+        off += l.cout;
+    }
+    // bf16 operand layouts for the tensor-core path: [Cout_pad][taps][Cin_pad], bias [Cout_pad]
+    for (int i = 1; i < kNumLayers; ++i) {
+        const LayerSpec &l = kLayers[i];
+        const int taps = l.k * l.k, cin_pad = pad_cin(l.cin), cout_pad = pad_cout(l.cout);
+        const size_t wbytes = (size_t)cout_pad * taps * cin_pad * 2;
+        if (!h->w_bf16[i]) CU_OK(h, cudaMalloc(&h->w_bf16[i], wbytes));
+        if (!h->b_pad[i]) CU_OK(h, cudaMalloc(&h->b_pad[i], (size_t)cout_pad * 4));
+        CU_OK(h, cudaMemset(h->w_bf16[i], 0, wbytes));
+        CU_OK(h, cudaMemset(h->b_pad[i], 0, (size_t)cout_pad * 4));
+        // rows = Cout*taps (valid output channels only), cols = Cin -> Cin_pad
+        CU_OK(h, launch_pack_bf16(h->blob + h->off_w[i], h->w_bf16[i], (long long)l.cout * taps, l.cin, cin_pad, 0));
+        CU_OK(h, cudaMemcpy(h->b_pad[i], h->blob + h->off_b[i], (size_t)l.cout * 4, cudaMemcpyDeviceToDevice));
+        if (cin_pad != l.cin) {   // fp32 copy with padded Cin for the CUDA-core paths (concat buffer pitch 64)
+            if (!h->w_f32pad[i]) CU_OK(h, cudaMalloc(&h->w_f32pad[i], (size_t)l.cout * taps * cin_pad * 4));
+            CU_OK(h, cudaMemset(h->w_f32pad[i], 0, (size_t)l.cout * taps * cin_pad * 4));
+            CU_OK(h, cudaMemcpy2D(h->w_f32pad[i], (size_t)cin_pad * 4, h->blob + h->off_w[i], (size_t)l.cin * 4,
+                                  (size_t)l.cin * 4, (size_t)l.cout * taps, cudaMemcpyDeviceToDevice));
+        }
+    }
+    CU_OK(h, cudaDeviceSynchronize());
+    h->has_weights = true;
+    return LWOP_OK;
+}
+
+int lwop_forward(lwop_handle *h, const float *in_dev, int batch, int mode, float *heat_dev, float *paf_dev,
+                 float *stage1_heat_dev, float *stage1_paf_dev, void *stream) {
+    FwdIO io{in_dev, 0, heat_dev, paf_dev, stage1_heat_dev, stage1_paf_dev};
+    return forward_impl(h, io, batch, mode, (cudaStream_t)stream);
+}
+
+int lwop_forward_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int mode, float *heat_dev, float *paf_dev,
+                    void *stream) {
+    FwdIO io{in_dev, 1, heat_dev, paf_dev, nullptr, nullptr};
+    return forward_impl(h, io, batch, mode, (cudaStream_t)stream);
+}
+
+int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int batch, int map_h, int map_w,
+                int img_h, int img_w, float thre1, double thre2, const lwop_decode_tables *t, void *stream) {
+    if (!h || !heat_dev || !paf_dev || !t || !t->counts || !t->joints || !t->limbs || !t->persons || !t->keypoints)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    if (map_h < 1 || map_w < 1 || img_h < map_h || img_w < map_w) return fail(h, LWOP_ERR_INVALID, "bad map size");
+    if ((long long)map_h * map_w > 16384) return fail(h, LWOP_ERR_UNSUPPORTED, "heat map larger than 16384 pixels");
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_decode_scratch(h);
+    if (rc != LWOP_OK) return rc;
+    DecodeArgs a{};
+    a.heat = heat_dev; a.paf = paf_dev; a.B = batch; a.h = map_h; a.w = map_w; a.H = img_h; a.W = img_w;
+    a.thre1 = thre1; a.thre2 = thre2; a.t = *t; a.peaks = h->peaks; a.peak_counts = h->peak_counts;
+    CU_OK(h, launch_decode(a, (cudaStream_t)stream, &h->launches));
+    return LWOP_OK;
+}
+
+int lwop_decode_fetch(lwop_handle *h, const lwop_decode_tables *t, int batch, const lwop_packed_tables *o,
+                      void *stream) {
+    if (!h || !t || !o || !o->counts) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_decode_scratch(h);
+    if (rc != LWOP_OK) return rc;
+    // worst case rows are bounded by the fixed capacities; size the packed device buffers for this batch
+    // lazily from the actual totals (phase 1: counts + offsets)
+    CU_OK(h, cudaMemcpyAsync(o->counts, t->counts, (size_t)batch * LWOP_COUNTS * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+    CU_OK(h, cudaStreamSynchronize(s));
+    size_t nj = 0, np = 0, nc = 0;
+    bool overflow = false;
+    for (int b = 0; b < batch; ++b) {
+        const int32_t *c = o->counts + (size_t)b * LWOP_COUNTS;
+        nj += c[0]; np += c[1]; nc += c[3];
+        overflow |= c[2] != 0;
+    }
+    if (nj > o->joints_cap || nc > o->limbs_cap || np > o->persons_cap)
+        return fail(h, LWOP_ERR_OVERFLOW, "host result buffers too small: need " + std::to_string(nj) + " joint, " +
+                                              std::to_string(nc) + " limb, " + std::to_string(np) + " person rows");
+    rc = ensure_pack_buffers(h, nj, nc, np);
+    if (rc != LWOP_OK) return rc;
+    CU_OK(h, launch_decode_pack(*t, batch, h->pack_offsets, h->pk_joints, h->pk_limbs, h->pk_persons,
+                                h->pk_keypoints, s, &h->launches));
+    if (nj) CU_OK(h, cudaMemcpyAsync(o->joints, h->pk_joints, nj * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (nc) CU_OK(h, cudaMemcpyAsync(o->limbs, h->pk_limbs, nc * 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (np) {
+        CU_OK(h, cudaMemcpyAsync(o->persons, h->pk_persons, np * 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_OK(h, cudaMemcpyAsync(o->keypoints, h->pk_keypoints, np * 42 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CU_OK(h, cudaStreamSynchronize(s));
+    if (overflow) return fail(h, LWOP_ERR_OVERFLOW, "a per-image decode table capacity was exceeded (counts[b][2])");
+    return LWOP_OK;
+}
+
+int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
+                    double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream) {
+    if (!h || !images_host || !o) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    const size_t in_bytes = (size_t)batch * h->H * h->W * 3 * (is_u8 ? 1 : 4);
+    const size_t cap_bytes = (size_t)h->max_batch * h->H * h->W * 3 * 4;
+    if (!h->stage_in) {
+        CU_OK(h, cudaMalloc(&h->stage_in, cap_bytes));
+        h->stage_in_bytes = cap_bytes;
+    }
+    const size_t px = (size_t)h->h8 * h->w8;
+    if (!h->stage_heat) {
+        CU_OK(h, cudaMalloc(&h->stage_heat, (size_t)h->max_batch * px * LWOP_NUM_JOINTS * 4));
+        CU_OK(h, cudaMalloc(&h->stage_paf, (size_t)h->max_batch * px * LWOP_NUM_PAFS * 4));
+    }
+    int rc = ensure_own_tables(h);
+    if (rc != LWOP_OK) return rc;
+    CU_OK(h, cudaMemcpyAsync(h->stage_in, images_host, in_bytes, cudaMemcpyHostToDevice, s));
+    FwdIO io{h->stage_in, is_u8, h->stage_heat, h->stage_paf, nullptr, nullptr};
+    rc = forward_impl(h, io, batch, mode, s);
+    if (rc != LWOP_OK) return rc;
+    rc = lwop_decode(h, h->stage_heat, h->stage_paf, batch, h->h8, h->w8, h->H, h->W, thre1, thre2, &h->own_tables,
+                     stream);
+    if (rc != LWOP_OK) return rc;
+    if (heat_host)
+        CU_OK(h, cudaMemcpyAsync(heat_host, h->stage_heat, (size_t)batch * px * LWOP_NUM_JOINTS * 4,
+                                 cudaMemcpyDeviceToHost, s));
+    if (paf_host)
+        CU_OK(h, cudaMemcpyAsync(paf_host, h->stage_paf, (size_t)batch * px * LWOP_NUM_PAFS * 4,
+                                 cudaMemcpyDeviceToHost, s));
+    return lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
+}
+
+int lwop_conv2d(lwop_handle *h, int mode, const void *in_dev, int in_dtype, int batch, int height, int width, int cin,
+                const float *w_dev, const float *bias_dev, int cout, int ksize, int stride, int dilation, int act,
+                const void *residual_dev, void *out_dev, int out_dtype, void *stream) {
+    if (!h || !in_dev || !w_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    if (mode != LWOP_MODE_BF16) {
+        ConvArgs a{};
+        a.in = in_dev; a.in_dtype = in_dtype; a.w = w_dev; a.bias = bias_dev; a.residual = residual_dev;
+        a.out = out_dev; a.out_dtype = out_dtype;
+        a.B = batch; a.H = height; a.W = width; a.Cin = cin; a.Cout = cout; a.ksize = ksize; a.stride = stride;
+        a.dil = dilation; a.act = act;
+        CU_OK(h, launch_conv_direct(a, s));
+        h->launches++;
+        return LWOP_OK;
+    }
+    // tensor-core path: stride-1 1x1 / 3x3 with bf16 input; weights are packed per call (unit-test entry)
+    if (in_dtype != LWOP_DT_BF16 || stride != 1 || (ksize != 1 && ksize != 3) || cin % 8 != 0)
+        return fail(h, LWOP_ERR_UNSUPPORTED, "tcgen05 conv needs bf16 input, stride 1, k in {1,3}, Cin % 8 == 0");
+    const int taps = ksize * ksize;
+    const int cin_pad = cin % 32 == 0 ? cin : ((cin + 63) / 64) * 64;
+    if (cin_pad != cin) return fail(h, LWOP_ERR_UNSUPPORTED, "tcgen05 conv entry needs Cin % 32 == 0 (pad the input)");
+    const int cout_pad = pad_cout(cout);
+    void *wp = nullptr;
+    float *bp = nullptr;
+    CU_OK(h, cudaMalloc(&wp, (size_t)cout_pad * taps * cin_pad * 2));
+    CU_OK(h, cudaMalloc(&bp, (size_t)cout_pad * 4));
+    CU_OK(h, cudaMemsetAsync(wp, 0, (size_t)cout_pad * taps * cin_pad * 2, s));
+    CU_OK(h, cudaMemsetAsync(bp, 0, (size_t)cout_pad * 4, s));
+    CU_OK(h, launch_pack_bf16(w_dev, wp, (long long)cout * taps, cin, cin_pad, s));
+    if (bias_dev) CU_OK(h, cudaMemcpyAsync(bp, bias_dev, (size_t)cout * 4, cudaMemcpyDeviceToDevice, s));
+    GemmConvDesc d{};
+    d.in = in_dev; d.w_packed = wp; d.bias = bp; d.residual = residual_dev; d.out = out_dev; d.out2 = nullptr;
+    d.out_dtype = out_dtype; d.lda = cin_pad; d.B = batch; d.H = height; d.W = width; d.Cin_pad = cin_pad;
+    d.Cout = cout; d.Cout_pad = cout_pad; d.ksize = ksize; d.dil = dilation; d.act = act; d.ldo = cout; d.out_col0 = 0;
+    d.ldr = cout;
+    char err[256];
+    GemmPlan *pl = gemm_plan_create(d, err, sizeof(err));
+    int rc = LWOP_OK;
+    if (!pl) {
+        rc = fail(h, LWOP_ERR_UNSUPPORTED, err);
+    } else {
+        cudaError_t e = gemm_plan_launch(pl, s);
+        h->launches += 2;
+        if (e != cudaSuccess) rc = fail(h, LWOP_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(e));
+        cudaError_t e2 = cudaStreamSynchronize(s);
+        if (rc == LWOP_OK && e2 != cudaSuccess)
+            rc = fail(h, LWOP_ERR_CUDA, std::string("gemm kernel: ") + cudaGetErrorString(e2));
+        gemm_plan_destroy(pl);
+    }
+    cudaFree(wp);
+    cudaFree(bp);
+    return rc;
+}
+
+int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype, int batch, int height, int width,
+                      int channels, const float *w_dev, int stride, int dilation, void *out_dev, void *stream) {
+    if (!h || !in_dev || !w_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    CU_OK(h, cudaSetDevice(h->device));
+    DwArgs a{};
+    a.in = in_dev; a.out = out_dev; a.dtype = dtype; a.w = w_dev;
+    a.B = batch; a.H = height; a.W = width; a.C = channels; a.stride = stride; a.dil = dilation;
+    if (mode == LWOP_MODE_BF16 && dtype == LWOP_DT_BF16) {
+        if (channels % 8 != 0 || !((stride == 1 && dilation <= 2) || (stride == 2 && dilation == 1)))
+            return fail(h, LWOP_ERR_UNSUPPORTED, "vector depthwise needs C % 8 == 0 and (s1,d1|d2) or (s2,d1)");
+        CU_OK(h, launch_depthwise_bf16(a, (cudaStream_t)stream));
+    } else {
+        CU_OK(h, launch_depthwise_simple(a, (cudaStream_t)stream));
+    }
+    h->launches++;
+    return LWOP_OK;
+}
+
+uint32_t lwop_crc32c(const void *data, size_t n) {
+    std::call_once(g_crc_once, crc_init);
+    const unsigned char *p = (const unsigned char *)data;
+    uint32_t crc = 0xFFFFFFFFu;
+    while (n >= 8) {
+        uint32_t lo, hi;
+        memcpy(&lo, p, 4);
+        memcpy(&hi, p + 4, 4);
+        lo ^= crc;
+        crc = g_crc_table[7][lo & 0xff] ^ g_crc_table[6][(lo >> 8) & 0xff] ^ g_crc_table[5][(lo >> 16) & 0xff] ^
+              g_crc_table[4][lo >> 24] ^ g_crc_table[3][hi & 0xff] ^ g_crc_table[2][(hi >> 8) & 0xff] ^
+              g_crc_table[1][(hi >> 16) & 0xff] ^ g_crc_table[0][hi >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n--) crc = g_crc_table[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+    return crc ^ 0xFFFFFFFFu;
+}
+
+long long lwop_launch_count(const lwop_handle *h, int reset) {
+    if (!h) return 0;
+    long long v = h->launches;
+    if (reset) const_cast<lwop_handle *>(h)->launches = 0;
+    return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+"""Host-side engine: owns one ``lwop_handle`` per (GPU, frame size), binds the
+checkpoint and exposes forward / decode / whole-path calls on torch tensors or
+host arrays.  PyTorch is used for device memory and streams only; all compute is
+in ``_lwop.so``.
+
+Reference protocol this replaces (reference ``test&eval/model_test.py:39-49,63-71``):
+build graph -> ``Saver.restore`` -> per frame ``sess.run([cpm, paf])`` -> ``decode_pose``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, checkpoint, graph
+
+_MODES = {"bf16": _lib.MODE_BF16, "fp32": _lib.MODE_FP32_CHECK, "fp32_check": _lib.MODE_FP32_CHECK,
+          "bf16_direct": _lib.MODE_BF16_DIRECT}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_gpu(device: int = 0) -> None:
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.LwopError(_lib.ERR_NO_DEVICE, "no CUDA device: the lwop path has no CPU fallback")
+    major, _ = torch.cuda.get_device_capability(device)
+    if major != 10:
+        raise _lib.LwopError(_lib.ERR_NO_DEVICE, "lwop kernels are built for sm_100a (B200) only")
+
+
+class DecodeResult:
+    """Per-image decode output in the reference's types (pose_decode.py:516-517)."""
+    __slots__ = ("joint_list", "person_to_joint_assoc", "joints", "limbs", "counts")
+
+    def __init__(self, joint_list, persons, joints, limbs, counts):
+        self.joint_list = joint_list
+        self.person_to_joint_assoc = persons
+        self.joints = joints
+        self.limbs = limbs
+        self.counts = counts
+
+
+def _split_packed(batch: int, counts: np.ndarray, joints: np.ndarray, limbs: np.ndarray,
+                  persons: np.ndarray, keypoints: np.ndarray) -> List[DecodeResult]:
+    out = []
+    oj = op = oc = 0
+    for b in range(batch):
+        c = counts[b]
+        nj, npers, nconn = int(c[0]), int(c[1]), int(c[3])
+        jl = joints[oj:oj + nj].copy() if nj else np.array([])          # shape (0,) when empty (:481)
+        pa = persons[op:op + npers].copy() if npers else np.array([])   # np.array([]) (:396)
+        kp = keypoints[op:op + npers].copy().reshape(-1, 42)
+        lim = []
+        o = oc
+        for t in range(_lib.NUM_LIMBS):
+            n = int(c[18 + t])
+            lim.append(limbs[o:o + n].copy())
+            o += n
+        out.append(DecodeResult(jl, pa, kp, lim, c.copy()))
+        oj += nj
+        op += npers
+        oc += nconn
+    return out
+
+
+class Engine:
+    """One per (device, H, W).  Not thread-safe: serialise calls per engine."""
+
+    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, use_graph: bool = True):
+        require_gpu(device)
+        self.lib = _lib.load()
+        self.device = device
+        self.height, self.width, self.max_batch = height, width, max_batch
+        self.map_h, self.map_w = graph.output_hw(height, width)
+        h = C.c_void_p()
+        flags = 0 if use_graph else _lib.FLAG_NO_GRAPH
+        _lib.check(self.lib.lwop_create(device, max_batch, height, width, flags, C.byref(h)))
+        self.handle = h
+        self.weights_source: Optional[str] = None
+        self._tables = None
+        self._host = None
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.lwop_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ---------------------------------------------------------------
+    def load_variables(self, variables: Dict[str, np.ndarray], source: str = "variables") -> None:
+        blob = graph.pack_blob(graph.fold_all(variables))
+        n = self.lib.lwop_weights_num_floats()
+        if blob.size != n:
+            raise ValueError(f"packed blob has {blob.size} floats, library expects {n}")
+        _lib.check(self.lib.lwop_load_weights(self.handle, blob.ctypes.data_as(C.c_void_p), blob.size), self.handle)
+        self.weights_source = source
+
+    def load_checkpoint(self, prefix: Optional[str] = None, seed: int = 61236) -> str:
+        variables, source = checkpoint.load_or_synthesize(prefix, seed)
+        self.load_variables(variables, source)
+        return source
+
+    # -- forward -----------------------------------------------------------------
+    def _stream(self) -> int:
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def forward(self, images, mode: str = "bf16", return_stage1: bool = False):
+        """images: CUDA tensor [B,H,W,3] float32 in [0,1] or uint8.  Returns
+        ``(heat [B,h,w,14], paf [B,h,w,26])`` float32 CUDA tensors (+ stage-1 maps)."""
+        torch = _torch()
+        if images.device.type != "cuda" or not images.is_contiguous():
+            raise ValueError("images must be a contiguous CUDA tensor")
+        B, H, W, Cc = images.shape
+        if (H, W, Cc) != (self.height, self.width, 3) or B > self.max_batch:
+            raise ValueError(f"engine built for [<= {self.max_batch},{self.height},{self.width},3], got {tuple(images.shape)}")
+        dev = images.device
+        heat = torch.empty((B, self.map_h, self.map_w, _lib.NUM_JOINTS), dtype=torch.float32, device=dev)
+        paf = torch.empty((B, self.map_h, self.map_w, _lib.NUM_PAFS), dtype=torch.float32, device=dev)
+        m = _MODES[mode]
+        if images.dtype == torch.uint8:
+            if return_stage1:
+                raise ValueError("stage-1 outputs need float32 input")
+            _lib.check(self.lib.lwop_forward_u8(self.handle, images.data_ptr(), B, m, heat.data_ptr(), paf.data_ptr(),
+                                                self._stream()), self.handle)
+            return heat, paf
+        if images.dtype != torch.float32:
+            raise ValueError("images must be float32 or uint8")
+        if return_stage1:
+            h1 = torch.empty_like(heat)
+            p1 = torch.empty_like(paf)
+            _lib.check(self.lib.lwop_forward(self.handle, images.data_ptr(), B, m, heat.data_ptr(), paf.data_ptr(),
+                                             h1.data_ptr(), p1.data_ptr(), self._stream()), self.handle)
+            return heat, paf, h1, p1
+        _lib.check(self.lib.lwop_forward(self.handle, images.data_ptr(), B, m, heat.data_ptr(), paf.data_ptr(),
+                                         None, None, self._stream()), self.handle)
+        return heat, paf
+
+    # -- decode ------------------------------------------------------------------
+    def _device_tables(self):
+        if self._tables is None:
+            torch = _torch()
+            B = self.max_batch
+            dev = torch.device("cuda", self.device)
+            t = {
+                "counts": torch.zeros((B, _lib.COUNTS), dtype=torch.int32, device=dev),
+                "joints": torch.empty((B, _lib.MAX_JOINTS, 6), dtype=torch.float64, device=dev),
+                "limbs": torch.empty((B, _lib.NUM_LIMBS, _lib.MAX_PEAKS, 5), dtype=torch.float64, device=dev),
+                "persons": torch.empty((B, _lib.MAX_PERSONS, 16), dtype=torch.float64, device=dev),
+                "keypoints": torch.empty((B, _lib.MAX_PERSONS, 42), dtype=torch.float32, device=dev),
+            }
+            s = _lib.DecodeTables(t["counts"].data_ptr(), t["joints"].data_ptr(), t["limbs"].data_ptr(),
+                                  t["persons"].data_ptr(), t["keypoints"].data_ptr())
+            self._tables = (t, s)
+        return self._tables
+
+    def _host_tables(self, batch: int):
+        """Pinned host result buffers, grown on demand."""
+        torch = _torch()
+        need_j, need_l, need_p = batch * 256, batch * 256, batch * 32
+        if self._host is None or self._host["batch"] < batch:
+            self._host = {
+                "batch": batch,
+                "counts": torch.zeros((batch, _lib.COUNTS), dtype=torch.int32).pin_memory(),
+                "joints": torch.empty((need_j, 6), dtype=torch.float64).pin_memory(),
+                "limbs": torch.empty((need_l, 5), dtype=torch.float64).pin_memory(),
+                "persons": torch.empty((need_p, 16), dtype=torch.float64).pin_memory(),
+                "keypoints": torch.empty((need_p, 42), dtype=torch.float32).pin_memory(),
+            }
+        return self._host
+
+    def _packed_struct(self, hst) -> _lib.PackedTables:
+        return _lib.PackedTables(hst["counts"].data_ptr(), hst["joints"].data_ptr(), hst["limbs"].data_ptr(),
+                                 hst["persons"].data_ptr(), hst["keypoints"].data_ptr(),
+                                 hst["joints"].shape[0], hst["limbs"].shape[0], hst["persons"].shape[0])
+
+    def _grow_host(self, hst, msg: str) -> bool:
+        """Overflow of the *host* buffers: double them and let the caller retry."""
+        if "host result buffers too small" not in msg:
+            return False
+        torch = _torch()
+        for k, w, dt in (("joints", 6, torch.float64), ("limbs", 5, torch.float64),
+                         ("persons", 16, torch.float64), ("keypoints", 42, torch.float32)):
+            hst[k] = torch.empty((hst[k].shape[0] * 4, w), dtype=dt).pin_memory()
+        return True
+
+    def decode_device(self, heat, paf, img_hw: Optional[Tuple[int, int]] = None, thre1: float = 0.1,
+                      thre2: float = 0.0) -> None:
+        """Runs the decode kernels on CUDA tensors ``heat [B,h,w,14]``, ``paf [B,h,w,26]``
+        (float32, contiguous); results stay in the engine's device tables."""
+        B, h, w, _ = heat.shape
+        if B > self.max_batch:
+            raise ValueError("batch exceeds engine capacity")
+        H, W = img_hw if img_hw is not None else (self.height, self.width)
+        _, s = self._device_tables()
+        _lib.check(self.lib.lwop_decode(self.handle, heat.data_ptr(), paf.data_ptr(), B, h, w, H, W,
+                                        float(np.float32(thre1)), float(thre2), C.byref(s), self._stream()),
+                   self.handle)
+
+    def fetch(self, batch: int) -> List[DecodeResult]:
+        _, s = self._device_tables()
+        hst = self._host_tables(batch)
+        while True:
+            p = self._packed_struct(hst)
+            rc = self.lib.lwop_decode_fetch(self.handle, C.byref(s), batch, C.byref(p), self._stream())
+            if rc == _lib.ERR_OVERFLOW:
+                msg = self.lib.lwop_last_error(self.handle).decode()
+                if self._grow_host(hst, msg):
+                    continue
+            _lib.check(rc, self.handle)
+            break
+        return _split_packed(batch, hst["counts"].numpy(), hst["joints"].numpy(), hst["limbs"].numpy(),
+                             hst["persons"].numpy(), hst["keypoints"].numpy())
+
+    def decode(self, heat, paf, img_hw: Optional[Tuple[int, int]] = None, thre1: float = 0.1,
+               thre2: float = 0.0) -> List[DecodeResult]:
+        self.decode_device(heat, paf, img_hw, thre1, thre2)
+        return self.fetch(heat.shape[0])
+
+    # -- whole path from host memory --------------------------------------------
+    def infer_host(self, images_host, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0,
+                   want_maps: bool = False):
+        """images_host: pinned (or pageable) CPU tensor / ndarray [B,H,W,3] float32 or uint8.
+        One C call: H2D, forward, decode, D2H.  Returns a list of DecodeResult
+        (and the host maps when ``want_maps``)."""
+        torch = _torch()
+        if isinstance(images_host, np.ndarray):
+            images_host = torch.from_numpy(np.ascontiguousarray(images_host))
+        B = images_host.shape[0]
+        is_u8 = images_host.dtype == torch.uint8
+        hst = self._host_tables(B)
+        heat_h = paf_h = None
+        if want_maps:
+            heat_h = torch.empty((B, self.map_h, self.map_w, _lib.NUM_JOINTS), dtype=torch.float32).pin_memory()
+            paf_h = torch.empty((B, self.map_h, self.map_w, _lib.NUM_PAFS), dtype=torch.float32).pin_memory()
+        while True:
+            p = self._packed_struct(hst)
+            rc = self.lib.lwop_infer_host(self.handle, images_host.data_ptr(), int(is_u8), B, _MODES[mode],
+                                          float(np.float32(thre1)), float(thre2), C.byref(p),
+                                          heat_h.data_ptr() if want_maps else None,
+                                          paf_h.data_ptr() if want_maps else None, self._stream())
+            if rc == _lib.ERR_OVERFLOW:
+                msg = self.lib.lwop_last_error(self.handle).decode()
+                if self._grow_host(hst, msg):
+                    continue
+            _lib.check(rc, self.handle)
+            break
+        res = _split_packed(B, hst["counts"].numpy(), hst["joints"].numpy(), hst["limbs"].numpy(),
+                            hst["persons"].numpy(), hst["keypoints"].numpy())
+        if want_maps:
+            return res, heat_h.numpy(), paf_h.numpy()
+        return res
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.lwop_launch_count(self.handle, int(reset)))
+
+
+# ---------------------------------------------------------------------------
+# process-wide engine cache used by the reference-shaped API in ``.src``
+# ---------------------------------------------------------------------------
+_engines: Dict[Tuple[int, int, int], Engine] = {}
+_engines_lock = threading.RLock()
+_variables: Optional[Dict[str, np.ndarray]] = None
+_variables_source: Optional[str] = None
+
+
+def set_variables(variables: Dict[str, np.ndarray], source: str = "variables") -> None:
+    """Bind the network weights for the reference-shaped API (replaces Saver.restore)."""
+    global _variables, _variables_source
+    _variables, _variables_source = variables, source
+    with _engines_lock:
+        for e in _engines.values():
+            e.load_variables(variables, source)
+
+
+def load_weights(prefix: Optional[str] = None, seed: int = 61236) -> str:
+    variables, source = checkpoint.load_or_synthesize(prefix, seed)
+    set_variables(variables, source)
+    return source
+
+
+def get_variables() -> Dict[str, np.ndarray]:
+    if _variables is None:
+        load_weights()
+    return _variables
+
+
+def get_engine(height: int, width: int, batch: int, device: int = 0) -> Engine:
+    key = (device, height, width)
+    with _engines_lock:
+        e = _engines.get(key)
+        if e is None or e.max_batch < batch:
+            if e is not None:
+                e.close()
+            e = Engine(height, width, max_batch=max(batch, 1), device=device)
+            e.load_variables(get_variables(), _variables_source or "variables")
+            _engines[key] = e
+        return e

@@ -1,0 +1,94 @@
+"""Whole-network parity on the GPU against the CPU oracle (oracle/forward_oracle.py):
+heatmaps and PAFs within max-abs 1e-4 in the fp32 check mode and 2e-2 in bf16
+(BASELINE.json north_star), at 368x368, 656x368 and 256x256."""
+import numpy as np
+import pytest
+import torch
+
+from lightweight_openpose_b200 import checkpoint, engine, synth
+from lightweight_openpose_b200.src.lightweight_openpose import lightweight_openpose
+from oracle.forward_oracle import ForwardOracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_BF16 = 2e-2
+
+
+@pytest.fixture(scope="module")
+def variables():
+    v, _ = checkpoint.load_or_synthesize()
+    engine.set_variables(v, "synthetic")
+    return v
+
+
+def _maxabs(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max())
+
+
+@pytest.mark.parametrize("hw,batch", [((368, 368), 2), ((368, 656), 1), ((256, 256), 3), ((250, 362), 1)])
+def test_forward_fp32_check_mode(variables, hw, batch):
+    x = synth.synth_batch(range(batch), hw[0], hw[1])
+    oh, op, oh1, op1 = ForwardOracle(variables)(x, return_stage1=True)
+    h, p, h1, p1 = lightweight_openpose(x, 14, 26, is_training=False, mode="fp32", return_stage1=True)
+    assert h.shape == oh.shape and p.shape == op.shape and h.dtype == np.float32
+    assert _maxabs(h1, oh1) <= TOL_FP32 and _maxabs(p1, op1) <= TOL_FP32
+    assert _maxabs(h, oh) <= TOL_FP32 and _maxabs(p, op) <= TOL_FP32
+
+
+@pytest.mark.parametrize("mode", ["bf16_direct", "bf16"])
+@pytest.mark.parametrize("hw,batch", [((368, 368), 2), ((368, 656), 1), ((256, 256), 3)])
+def test_forward_bf16(variables, hw, batch, mode):
+    x = synth.synth_batch(range(10, 10 + batch), hw[0], hw[1])
+    oh, op, oh1, op1 = ForwardOracle(variables)(x, return_stage1=True)
+    h, p, h1, p1 = lightweight_openpose(x, 14, 26, is_training=False, mode=mode, return_stage1=True)
+    errs = (_maxabs(h1, oh1), _maxabs(p1, op1), _maxabs(h, oh), _maxabs(p, op))
+    print(mode, hw, "max-abs", errs)
+    assert max(errs) <= TOL_BF16, errs
+
+
+def test_forward_batch64_matches_oracle_and_is_batch_invariant(variables):
+    """config[1]: batch 64, bf16 against the oracle; each image's result must not
+    depend on its batch mates (replica sharding relies on it)."""
+    x = synth.synth_batch(range(64), 368, 368)
+    xd = torch.from_numpy(x).cuda()
+    h, p = lightweight_openpose(xd, 14, 26, is_training=False)
+    h, p = h.cpu().numpy(), p.cpu().numpy()
+    oh, op = ForwardOracle(variables)(x[:8])
+    assert _maxabs(h[:8], oh) <= TOL_BF16 and _maxabs(p[:8], op) <= TOL_BF16
+    h2, p2 = lightweight_openpose(xd[37:41].contiguous(), 14, 26, is_training=False)
+    assert np.array_equal(h2.cpu().numpy(), h[37:41]) and np.array_equal(p2.cpu().numpy(), p[37:41])
+
+
+def test_eager_net_factory_path_matches_executor(variables):
+    x = synth.synth_batch([3], 256, 256)
+    h, p = lightweight_openpose(x, 14, 26, is_training=False, mode="fp32")
+    he, pe = lightweight_openpose(x, 14, 26, is_training=False, mode="fp32", eager=True)
+    assert _maxabs(h, he) <= 1e-5 and _maxabs(p, pe) <= 1e-5
+    hb, pb = lightweight_openpose(x, 14, 26, is_training=False, mode="bf16")
+    hbe, pbe = lightweight_openpose(x, 14, 26, is_training=False, mode="bf16", eager=True)
+    assert _maxabs(hb, hbe) <= TOL_BF16 and _maxabs(pb, pbe) <= TOL_BF16
+
+
+def test_uint8_input_path(variables):
+    u8 = np.stack([synth.synth_image(s, 256, 256) for s in (0, 1)])
+    xf = (u8 / 255.).astype(np.float32)
+    eng = engine.get_engine(256, 256, 2)
+    hu, pu = eng.forward(torch.from_numpy(u8).cuda())
+    hf, pf = eng.forward(torch.from_numpy(xf).cuda())
+    assert torch.equal(hu, hf) and torch.equal(pu, pf)
+    hu32, _ = eng.forward(torch.from_numpy(u8).cuda(), mode="fp32")
+    hf32, _ = eng.forward(torch.from_numpy(xf).cuda(), mode="fp32")
+    assert torch.equal(hu32, hf32)
+
+
+def test_graph_replay_is_deterministic_and_counts_launches(variables):
+    x = torch.from_numpy(synth.synth_batch([5, 6], 368, 368)).cuda()
+    eng = engine.get_engine(368, 368, 2)
+    a = eng.forward(x)
+    eng.launch_count(reset=True)
+    b = eng.forward(x)
+    n = eng.launch_count()
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert n >= 57          # 57 convs -> at least as many kernels per forward

@@ -1,0 +1,145 @@
+"""Per-kernel parity on the GPU through the C ABI: every CUDA conv kernel against
+a plain torch-CPU reference of the same op (float64 math on the same bf16-rounded
+inputs), over the distinct (Cin, Cout, k, stride, dil, H, W) of the network
+ including odd sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from lightweight_openpose_b200 import _lib, engine
+from util import bf16_round, ref_conv_nhwc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return engine.Engine(16, 16, max_batch=1, device=0, use_graph=False)
+
+
+def _conv(eng, mode, x, w, b, k, stride, dil, act, res, out_dtype):
+    B, H, W, cin = x.shape
+    cout = w.shape[0]
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    out = torch.empty((B, Ho, Wo, cout), dtype=out_dtype, device="cuda")
+    dt = lambda t: _lib.DT_F32 if t.dtype == torch.float32 else _lib.DT_BF16
+    rc = eng.lib.lwop_conv2d(eng.handle, mode, x.data_ptr(), dt(x), B, H, W, cin, w.data_ptr(),
+                             b.data_ptr() if b is not None else None, cout, k, stride, dil, act,
+                             res.data_ptr() if res is not None else None, out.data_ptr(), dt(out),
+                             torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, eng.handle)
+    torch.cuda.synchronize()
+    return out
+
+
+FP32_CASES = [
+    # B, H, W, cin, cout, k, stride, dil, act, residual
+    (2, 37, 29, 3, 32, 3, 2, 1, 1, False),      # first conv, odd size
+    (1, 23, 23, 128, 128, 3, 1, 2, 1, True),    # refinement dil-2 conv + residual
+    (1, 16, 19, 40, 128, 1, 1, 1, 1, False),
+    (2, 9, 9, 512, 14, 1, 1, 1, 0, False),
+    (1, 12, 10, 128, 128, 1, 1, 1, 2, True),    # ELU + add
+]
+
+
+@pytest.mark.parametrize("case", FP32_CASES)
+def test_conv_fp32_check_kernel(eng, case):
+    B, H, W, cin, cout, k, stride, dil, act, use_res = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    x = rng.normal(size=(B, H, W, cin)).astype(np.float32)
+    w = (rng.normal(size=(cout, k * k, cin)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.normal(size=(cout,)).astype(np.float32)
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    res = rng.normal(size=(B, Ho, Wo, cout)).astype(np.float32) if use_res else None
+    got = _conv(eng, _lib.MODE_FP32_CHECK, torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(),
+                torch.from_numpy(b).cuda(), k, stride, dil, act,
+                torch.from_numpy(res).cuda() if use_res else None, torch.float32).cpu().numpy()
+    want = ref_conv_nhwc(x, w, b, k, stride, dil, act, res)
+    assert np.abs(got - want).max() <= 2e-5
+
+
+TC_CASES = [
+    # B, H, W, cin, cout, k, dil, act, residual, out_f32
+    (1, 16, 16, 64, 128, 1, 1, 1, False, False),     # one full M tile pair, K = 64
+    (2, 23, 23, 128, 128, 1, 1, 1, False, False),    # M tail
+    (3, 46, 46, 512, 512, 1, 1, 1, False, False),    # largest GEMM, two N tiles of 256
+    (2, 46, 46, 256, 256, 1, 1, 1, False, False),
+    (1, 92, 92, 32, 64, 1, 1, 1, False, False),      # K = 32 (64B swizzle)
+    (2, 23, 31, 128, 256, 1, 1, 1, False, False),
+    (2, 46, 46, 512, 128, 1, 1, 1, False, False),
+    (2, 23, 23, 128, 128, 1, 1, 2, True, False),     # ELU + residual
+    (2, 23, 23, 512, 14, 1, 1, 0, False, True),      # narrow linear head, fp32 out
+    (2, 23, 23, 128, 26, 1, 1, 0, False, True),
+    (2, 23, 23, 64, 128, 1, 1, 1, False, False),
+    (1, 16, 16, 128, 128, 3, 1, 1, False, False),    # 3x3 im2col
+    (2, 46, 46, 128, 128, 3, 1, 1, False, False),
+    (2, 46, 46, 128, 128, 3, 2, 1, True, False),     # dilation 2 + residual
+    (3, 23, 37, 128, 128, 3, 2, 1, False, False),    # non-square, image-boundary-crossing tiles
+    (1, 7, 5, 128, 128, 3, 1, 1, False, False),      # tiny tensor (< 128 KiB im2col map workaround)
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_kernel(eng, case):
+    B, H, W, cin, cout, k, dil, act, use_res, out_f32 = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    x = bf16_round(rng.normal(size=(B, H, W, cin)))
+    w = bf16_round(rng.normal(size=(cout, k * k, cin)) / np.sqrt(k * k * cin))
+    b = rng.normal(size=(cout,)).astype(np.float32)
+    res = bf16_round(rng.normal(size=(B, H, W, cout))) if use_res else None
+    got = _conv(eng, _lib.MODE_BF16, torch.from_numpy(x).cuda().to(torch.bfloat16), torch.from_numpy(w).cuda(),
+                torch.from_numpy(b).cuda(), k, 1, dil, act,
+                torch.from_numpy(res).cuda().to(torch.bfloat16) if use_res else None,
+                torch.float32 if out_f32 else torch.bfloat16).float().cpu().numpy()
+    want = ref_conv_nhwc(x, w, b, k, 1, dil, act, res)
+    tol = 2e-4 if out_f32 else 2.0 ** -8 * max(1.0, float(np.abs(want).max()))   # bf16 output rounding
+    err = np.abs(got - want)
+    assert err.max() <= tol, (err.max(), tol, np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("case", [(2, 23, 23, 128, 128, 3, 2, 1, True), (1, 20, 17, 64, 128, 1, 1, 2, False)])
+def test_conv_bf16_direct_kernel(eng, case):
+    B, H, W, cin, cout, k, dil, act, use_res = case
+    rng = np.random.default_rng(7)
+    x = bf16_round(rng.normal(size=(B, H, W, cin)))
+    w = (rng.normal(size=(cout, k * k, cin)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.normal(size=(cout,)).astype(np.float32)
+    res = bf16_round(rng.normal(size=(B, H, W, cout))) if use_res else None
+    got = _conv(eng, _lib.MODE_BF16_DIRECT, torch.from_numpy(x).cuda().to(torch.bfloat16), torch.from_numpy(w).cuda(),
+                torch.from_numpy(b).cuda(), k, 1, dil, act,
+                torch.from_numpy(res).cuda().to(torch.bfloat16) if use_res else None,
+                torch.bfloat16).float().cpu().numpy()
+    want = ref_conv_nhwc(x, w, b, k, 1, dil, act, res)
+    assert np.abs(got - want).max() <= 2.0 ** -8 * max(1.0, float(np.abs(want).max()))
+
+
+DW_CASES = [
+    # B, H, W, C, stride, dil
+    (2, 184, 184, 32, 1, 1), (1, 184, 184, 64, 2, 1), (1, 92, 92, 128, 1, 1), (2, 92, 92, 128, 2, 1),
+    (1, 46, 46, 256, 1, 1), (2, 46, 46, 512, 1, 2), (1, 45, 37, 128, 2, 1), (1, 23, 41, 512, 1, 2),
+    (1, 33, 33, 64, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES)
+@pytest.mark.parametrize("vec", [True, False])
+def test_depthwise_kernels(eng, case, vec):
+    B, H, W, Cc, stride, dil = case
+    rng = np.random.default_rng(11)
+    x = bf16_round(rng.normal(size=(B, H, W, Cc)))
+    w = (rng.normal(size=(9, Cc)) / 3.0).astype(np.float32)
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    xd = torch.from_numpy(x).cuda()
+    if vec:
+        xd = xd.to(torch.bfloat16)
+    out = torch.empty((B, Ho, Wo, Cc), dtype=xd.dtype, device="cuda")
+    rc = eng.lib.lwop_depthwise3x3(eng.handle, _lib.MODE_BF16 if vec else _lib.MODE_FP32_CHECK, xd.data_ptr(),
+                                   _lib.DT_BF16 if vec else _lib.DT_F32, B, H, W, Cc, torch.from_numpy(w).cuda().data_ptr(),
+                                   stride, dil, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, eng.handle)
+    torch.cuda.synchronize()
+    want = ref_conv_nhwc(x, w, None, 3, stride, dil, 0, depthwise=True)
+    tol = 2.0 ** -8 * max(1.0, float(np.abs(want).max())) if vec else 1e-5
+    assert np.abs(out.float().cpu().numpy() - want).max() <= tol
