@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the lightweight_openpose hot path: 368x368 forward + decode images/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One process per GPU (under torchrun for N > 1; ranks are independent replicas,
+the only cross-rank traffic is the barrier and the max-reduction of the time).
+A step is one pass of the whole path -- network forward (bf16 tensor-core
+kernels) + on-device pose decode -- over one batch of synthetic frames.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "368x368 forward+decode images/sec"
+H = W = 368
+PARAM = {"thre1": 0.1, "thre2": 0.0}
+
+# algorithmic work per 368x368 image
+GFLOP_TOTAL = 17.639
+GFLOP_TENSOR = 17.453
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_frames(batch: int, distinct: int = 32):
+    """[batch, H, W, 3] uint8 synthetic frames: `distinct` seeded frames, tiled."""
+    from lightweight_openpose_b200 import synth
+    base = np.stack([synth.synth_image(s, H, W) for s in range(distinct)])
+    reps = -(-batch // distinct)
+    return np.concatenate([base] * reps)[:batch]
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path (torch-CPU forward + numpy/cv2 decode)
+# ---------------------------------------------------------------------------
+def cpu_path_images_per_s(n_images: int, threads: int):
+    import torch
+    from lightweight_openpose_b200 import checkpoint, synth
+    from oracle.forward_oracle import ForwardOracle
+    from oracle import decode_oracle
+    torch.set_num_threads(threads)
+    variables, _ = checkpoint.load_or_synthesize()
+    orc = ForwardOracle(variables)
+    frames = [synth.synth_image(s, H, W) for s in range(n_images)]
+    img0 = np.zeros((H, W, 3), np.uint8)
+    orc((frames[0] / 255.).astype(np.float32)[None])          # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    for f in frames:                                          # serial per-frame loop, like model_test.py:82-99
+        x = (f / 255.).astype(np.float32)[None]
+        heat, paf = orc(x)
+        decode_oracle.decode(img0, PARAM, heat[0], paf[0], draw=False)
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(2, min(args.cpu_images, 160 // max(args.steps, 1)))     # keep the whole run to a few minutes
+    vals = []
+    for _ in range(args.warmup):
+        cpu_path_images_per_s(1, threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_path_images_per_s(sample, threads)
+        vals.append(v)
+        t_total += dt
+    value = sample * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"368x368 forward+decode, batch-1 serial loop over {sample} synthetic frames per step "
+                               "(CPU port of the reference path: torch-CPU fp32 forward, all host threads, + "
+                               "numpy/cv2 decode, single thread as in the reference loop); stand-in for TF-CPU, "
+                               "TensorFlow is not installable here"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames x {args.steps} steps"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def classify_step(desc):
+    layer, is_dw, h, w, cin, cout, k, stride, dil, tc = desc
+    if is_dw:
+        return "depthwise3x3"
+    if layer == 0:
+        return "conv1_3x3s2"
+    return "gemm_conv3x3_im2col" if k == 3 else "gemm_conv1x1"
+
+
+def step_work(desc, batch):
+    """(flops, algorithmic bytes) of one step for `batch` images (bf16 activations)."""
+    layer, is_dw, h, w, cin, cout, k, stride, dil, tc = desc
+    oh, ow = -(-h // stride), -(-w // stride)
+    if is_dw:
+        return 2.0 * 9 * oh * ow * cin * batch, 2.0 * (h * w * cin + oh * ow * cin) * batch
+    flops = 2.0 * oh * ow * cout * cin * k * k * batch
+    in_b = (4 if layer == 0 else 2) * h * w * cin
+    out_b = (4 if cout in (14, 26) else 2) * oh * ow * cout
+    return flops, float(in_b + out_b) * batch
+
+
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import torch
+    from lightweight_openpose_b200 import checkpoint, engine
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    batch = args.batch
+    eng = engine.Engine(H, W, max_batch=batch, device=local_rank)
+    variables, source = checkpoint.load_or_synthesize()
+    eng.load_variables(variables, source)
+
+    frames_u8 = make_frames(batch)
+    x_host = torch.from_numpy((frames_u8 / 255.).astype(np.float32)).pin_memory()      # reference feed: img / 255.
+    x_dev = x_host.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        heat, paf = eng.forward(x_dev, mode=args.mode)
+        eng.decode_device(heat, paf, (H, W), PARAM["thre1"], PARAM["thre2"])
+        return heat, paf
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = eng.launch_count()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    res = eng.fetch(batch)               # untimed: decode load of the workload, for the config record
+    joints_per_img = float(np.mean([r.counts[0] for r in res]))
+    persons_per_img = float(np.mean([r.counts[1] for r in res]))
+
+    # ---- end to end through the host-buffer C entry (lwop_infer_host) ----
+    for _ in range(max(1, min(args.warmup, 3))):
+        eng.infer_host(x_host, mode=args.mode)
+    barrier()
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    d2h = 0
+    for _ in range(args.steps):
+        out = eng.infer_host(x_host, mode=args.mode)
+    ee1.record()
+    barrier()
+    e2e_ms = ee0.elapsed_time(ee1)                 # device clock; infer_host synchronises every step
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    d2h = int(batch * 32 * 4 + sum(r.joint_list.size * 8 + r.person_to_joint_assoc.size * 8 + r.joints.size * 4
+                                   + sum(l.size for l in r.limbs) * 8 for r in out))
+    h2d = int(x_host.numel() * 4)
+
+    # uint8 frames (the reference's frames before `/255.`): 4x less H2D, normalised on the device
+    u8_host = torch.from_numpy(frames_u8).pin_memory()
+    eng.infer_host(u8_host, mode=args.mode)
+    barrier()
+    eu0, eu1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eu0.record()
+    for _ in range(args.steps):
+        eng.infer_host(u8_host, mode=args.mode)
+    eu1.record()
+    barrier()
+    e2e_u8_ms = eu0.elapsed_time(eu1)
+
+    # ---- max over ranks ----
+    t = torch.tensor([ms_total, e2e_ms, e2e_u8_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, e2e_u8_ms = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        # ---- live per-kernel timing for the roofline (rank 0 only, outside the timed loops) ----
+        descs = eng.step_descs()
+        acc = np.zeros(len(descs))
+        n_prof = 5
+        eng.profile_forward(x_dev, mode=args.mode)
+        for _ in range(n_prof):
+            acc += np.asarray(eng.profile_forward(x_dev, mode=args.mode))
+        acc /= n_prof
+        classes = {}
+        for d, ms in zip(descs, acc):
+            c = classes.setdefault(classify_step(d), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            fl, by = step_work(d, batch)
+            c["ms"] += ms
+            c["flops"] += fl
+            c["bytes"] += by
+            c["launches"] += 1
+        peaks = measured_peaks()
+        dom = max(classes, key=lambda k: classes[k]["ms"])
+        dc = classes[dom]
+        if dom.startswith("gemm"):
+            achieved = dc["flops"] / (dc["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
+        else:
+            achieved = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+        roof["kernel"] = dom
+        roof["launches_per_step"] = dc["launches"]
+        roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
+        roof["peak_source"] = peaks["source"] + (" (sustained)" if dom.startswith("gemm") else "")
+        per_class = {}
+        for k, c in classes.items():
+            per_class[k] = {"ms": round(c["ms"], 4), "launches": c["launches"],
+                            "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 2),
+                            "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)}
+        fwd_ms = float(acc.sum())
+
+        # ---- CPU baseline on a bounded sample (rank 0, N = 1 contract; cheap enough to always run) ----
+        cpu = None
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_path_images_per_s(args.cpu_images, threads)
+            cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_images} synthetic 368x368 frames, batch-1 serial forward (torch-CPU fp32, "
+                             f"{threads} threads) + decode (numpy/cv2, 1 thread), {dt:.1f} s"}
+
+        ms_per_step = ms_total / args.steps
+        total_images = batch * world * args.steps
+        value = total_images / (ms_total * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"batch {batch} per GPU, 368x368 forward+decode (BASELINE.json configs[2]), "
+                            f"{world} independent replica(s), no collective on the data path",
+                "global_batch": batch * world, "height": H, "width": W, "mode": args.mode,
+                "weights": source, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
+                "l2": f"inputs {x_dev.numel() * 4 / 2**20:.0f} MiB fp32 per step > 126 MB L2 (no flush needed)",
+                "decode_load": {"joints_per_image": joints_per_img, "persons_per_image": persons_per_img},
+                "forward_ms_sum_of_kernels": round(fwd_ms, 3),
+                "forward_tflops_tensor": round(GFLOP_TENSOR * batch / fwd_ms, 1) if fwd_ms > 0 else None,
+                "kernel_classes": per_class,
+                "e2e_uint8_frames": {"value": total_images / (e2e_u8_ms * 1e-3), "unit": "images/s",
+                                     "h2d_bytes_per_step": int(u8_host.numel())},
+                "e2e_wall_ms_per_step": e2e_wall_ms / args.steps,
+            },
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_images / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
+    ap.add_argument("--cpu-images", type=int, default=16, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        args.warmup = min(args.warmup, 2)        # each warm-up is one full CPU frame
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it so that there is one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,16 @@ int lwop_same_out(int in, int stride);
 /* CRC32C (Castagnoli) for TensorBundle verification; host function. */
 uint32_t lwop_crc32c(const void *data, size_t nbytes);
 
+/* Layer program introspection and per-kernel timing (bench.py's live roofline).
+ * lwop_step_desc fills out[10] = {layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, uses_tcgen05}.
+ * lwop_profile_forward runs one forward WITHOUT the CUDA graph, bracketing every
+ * kernel with CUDA events on `stream`, synchronises and writes the per-step
+ * durations in milliseconds to step_ms[lwop_num_steps()]. */
+int lwop_num_steps(const lwop_handle *h);
+int lwop_step_desc(const lwop_handle *h, int step, int *out10);
+int lwop_profile_forward(lwop_handle *h, const float *in_dev, int batch, int mode,
+                         float *heat_dev, float *paf_dev, float *step_ms, void *stream);
+
 /* number of kernel launches issued by this handle since creation / last reset */
 long long lwop_launch_count(const lwop_handle *h, int reset);
 

@@ -23,6 +23,7 @@ constexpr int kRadius = 5;          // dis_thres, pose_decode.py:53
 constexpr int kPatchHalf = 2;       // win_size,  pose_decode.py:141
 constexpr int kSamples = 10;        // num_intermed_pts, pose_decode.py:188
 constexpr int kMaxPixPerThread = 64;
+constexpr int kMaxWorkPersons = LWOP_NUM_LIMBS * LWOP_MAX_PEAKS;   // one new person per connection at most
 
 // cv2 interpolateCubic, A = -0.75, float32, no contraction
 __device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
@@ -361,9 +362,10 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
 __global__ void __launch_bounds__(32)
 group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_counts, const double *__restrict__ limbs,
              int *__restrict__ counts, double *__restrict__ joints, double *__restrict__ persons,
-             float *__restrict__ keypoints) {
+             float *__restrict__ keypoints, double *__restrict__ work) {
     const int b = blockIdx.x, lane = threadIdx.x;
-    __shared__ double P[LWOP_MAX_PERSONS][16];
+    // working list of persons before the final filter: at most one new person per connection
+    double (*P)[16] = reinterpret_cast<double (*)[16]>(work + (long long)b * kMaxWorkPersons * 16);
     __shared__ int s_off[LWOP_NUM_JOINTS + 1];
     const int *pc = peak_counts + b * 16;
     int *cnt = counts + b * LWOP_COUNTS;
@@ -444,7 +446,7 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                     P[m0][14] += __dadd_rn(js_b, s);
                 }
             } else {                                              // 0 or >= 3 matches: new person (:367-379)
-                if (np < LWOP_MAX_PERSONS) {
+                if (np < kMaxWorkPersons) {
                     if (lane < 14) P[np][lane] = lane == ja ? a_id : (lane == jb ? b_id : -1.0);
                     if (lane == 15) P[np][15] = 2.0;
                     if (lane == 14) {
@@ -457,6 +459,7 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                 }
             }
             __syncwarp();
+            __threadfence_block();
         }
     }
     // drop persons with < 3 parts or mean score < 0.2 (:382-391); keypoint table (:403-429)
@@ -466,6 +469,10 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     for (int k = 0; k < np; ++k) {
         const bool drop = P[k][15] < 3.0 || (P[k][14] / P[k][15]) < 0.2;
         if (drop) continue;
+        if (kept >= LWOP_MAX_PERSONS) {
+            overflow = true;
+            break;
+        }
         if (lane < 16) po[kept * 16 + lane] = P[k][lane];
         for (int e = lane; e < 42; e += 32) ko[kept * 42 + e] = 0.0f;
         __syncwarp();
@@ -564,6 +571,8 @@ __global__ void zero_counts_kernel(int *counts, int n) {
 
 }  // namespace
 
+size_t decode_scratch_work_bytes(int B) { return (size_t)B * kMaxWorkPersons * 16 * sizeof(double); }
+
 size_t decode_scratch_peaks_bytes(int B) {
     return (size_t)B * LWOP_NUM_JOINTS * LWOP_MAX_PEAKS * 4 * sizeof(float);
 }
@@ -594,7 +603,7 @@ cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launch
     limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), 128, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, a.peaks,
                                                            a.peak_counts, a.t.limbs, a.t.counts);
     group_kernel<<<a.B, 32, 0, s>>>(a.peaks, a.peak_counts, a.t.limbs, a.t.counts, a.t.joints, a.t.persons,
-                                    a.t.keypoints);
+                                    a.t.keypoints, a.work);
     if (launches) *launches += 4;
     return cudaGetLastError();
 }

@@ -172,11 +172,12 @@ template <int STRIDE, int DIL>
 __global__ void __launch_bounds__(256)
 depthwise_bf16_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, uint4 *__restrict__ out, int B,
                       int H, int W, int C8, int Ho, int Wo, int pad_t, int pad_l, int strip) {
-    // thread -> (channel group cg, strip sx, row oy, image b)
-    const int cg = blockIdx.x * blockDim.x + threadIdx.x;      // fastest: channel groups (coalesced)
+    // thread -> (channel group cg, strip sx, row oy, image b); blockIdx.x = work item * cblocks + channel block
+    const int cblocks = (C8 + blockDim.x - 1) / blockDim.x;
+    const int cg = (blockIdx.x % cblocks) * blockDim.x + threadIdx.x;      // fastest: channel groups (coalesced)
     if (cg >= C8) return;
     const int nstrips = (Wo + strip - 1) / strip;
-    int t = blockIdx.y;
+    int t = blockIdx.x / cblocks;
     const int sx = t % nstrips;
     t /= nstrips;
     const int oy = t % Ho;
@@ -234,7 +235,9 @@ cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s) {
     const int threads = C8 >= 64 ? 64 : 32;
     const int strip = 8;
     const int nstrips = (pw.out + strip - 1) / strip;
-    dim3 grid((C8 + threads - 1) / threads, (unsigned)(a.B * ph.out * nstrips));
+    const long long nblocks = (long long)((C8 + threads - 1) / threads) * a.B * ph.out * nstrips;
+    if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)nblocks);
 #define LWOP_DW(S, D)                                                                                          \
     depthwise_bf16_kernel<S, D><<<grid, threads, 0, s>>>((const uint4 *)a.in, a.w, (uint4 *)a.out, a.B, a.H,    \
                                                          a.W, C8, ph.out, pw.out, ph.before, pw.before, strip)

@@ -73,9 +73,11 @@ struct DecodeArgs {
     // scratch owned by the handle
     float *peaks;        // [B][14][LWOP_MAX_PEAKS][4]  (x, y, score, unused) in kept order
     int *peak_counts;    // [B][16]
+    double *work;        // [B][13*LWOP_MAX_PEAKS][16] working list of persons (grouping)
 };
 cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launches);
 size_t decode_scratch_peaks_bytes(int B);
+size_t decode_scratch_work_bytes(int B);
 // compaction of the fixed-capacity tables: offsets[b][4] = exclusive prefix of (joints, persons, conns, 0)
 cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,
                                double *limbs_packed, double *persons_packed, float *keypoints_packed,

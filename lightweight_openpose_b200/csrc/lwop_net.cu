@@ -123,6 +123,7 @@ struct lwop_handle {
     // decode scratch
     float *peaks = nullptr;
     int *peak_counts = nullptr;
+    double *group_work = nullptr;
     int *pack_offsets = nullptr;
     double *pk_joints = nullptr, *pk_limbs = nullptr, *pk_persons = nullptr;
     float *pk_keypoints = nullptr;
@@ -308,8 +309,9 @@ struct FwdIO {
     float *heat, *paf, *h1, *p1;
 };
 
-// Issue every kernel of one forward pass on `s`.
-int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream_t s) {
+// Issue every kernel of one forward pass on `s`.  With `ev` (2 events per step)
+// every step is bracketed by event records for per-kernel timing.
+int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream_t s, cudaEvent_t *ev = nullptr) {
     const bool f32 = mode == LWOP_MODE_FP32_CHECK;
     void **arena = f32 ? h->arena_f32 : h->arena_bf16;
     const int dt = f32 ? LWOP_DT_F32 : LWOP_DT_BF16;
@@ -329,9 +331,15 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
         h->launches++;
         in_f32 = (const float *)h->arena_f32[B_IN];
     }
+    struct EvGuard {
+        cudaEvent_t *ev; size_t i; cudaStream_t s;
+        EvGuard(cudaEvent_t *e, size_t idx, cudaStream_t st) : ev(e), i(idx), s(st) { if (ev) cudaEventRecord(ev[2 * i], s); }
+        ~EvGuard() { if (ev) cudaEventRecord(ev[2 * i + 1], s); }
+    };
     for (size_t i = 0; i < h->steps.size(); ++i) {
         const Step &st = h->steps[i];
         const LayerSpec &l = kLayers[st.layer];
+        EvGuard guard(ev, i, s);
         void *out = st.out == B_HEAT ? (void *)io.heat : st.out == B_PAF ? (void *)io.paf : arena[st.out];
         const void *in = st.in == B_IN ? (const void *)in_f32 : arena[st.in];
         float *out2 = st.out2 == B_H1 ? io.h1 : st.out2 == B_P1 ? io.p1 : nullptr;
@@ -442,6 +450,7 @@ int ensure_decode_scratch(lwop_handle *h) {
     if (h->peaks) return LWOP_OK;
     CU_OK(h, cudaMalloc(&h->peaks, decode_scratch_peaks_bytes(h->max_batch)));
     CU_OK(h, cudaMalloc(&h->peak_counts, (size_t)h->max_batch * 16 * sizeof(int)));
+    CU_OK(h, cudaMalloc(&h->group_work, decode_scratch_work_bytes(h->max_batch)));
     CU_OK(h, cudaMalloc(&h->pack_offsets, ((size_t)h->max_batch + 1) * 4 * sizeof(int)));
     CU_OK(h, cudaMallocHost(&h->h_offsets, ((size_t)h->max_batch + 1) * 4 * sizeof(int)));
     return LWOP_OK;
@@ -572,6 +581,7 @@ int lwop_destroy(lwop_handle *h) {
     if (h->blob) cudaFree(h->blob);
     if (h->peaks) cudaFree(h->peaks);
     if (h->peak_counts) cudaFree(h->peak_counts);
+    if (h->group_work) cudaFree(h->group_work);
     if (h->pack_offsets) cudaFree(h->pack_offsets);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
     if (h->pk_joints) cudaFree(h->pk_joints);
@@ -660,7 +670,7 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
     if (rc != LWOP_OK) return rc;
     DecodeArgs a{};
     a.heat = heat_dev; a.paf = paf_dev; a.B = batch; a.h = map_h; a.w = map_w; a.H = img_h; a.W = img_w;
-    a.thre1 = thre1; a.thre2 = thre2; a.t = *t; a.peaks = h->peaks; a.peak_counts = h->peak_counts;
+    a.thre1 = thre1; a.thre2 = thre2; a.t = *t; a.peaks = h->peaks; a.peak_counts = h->peak_counts; a.work = h->group_work;
     CU_OK(h, launch_decode(a, (cudaStream_t)stream, &h->launches));
     return LWOP_OK;
 }
@@ -828,6 +838,47 @@ uint32_t lwop_crc32c(const void *data, size_t n) {
     }
     while (n--) crc = g_crc_table[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
     return crc ^ 0xFFFFFFFFu;
+}
+
+int lwop_num_steps(const lwop_handle *h) { return h ? (int)h->steps.size() : 0; }
+
+int lwop_step_desc(const lwop_handle *h, int step, int *out10) {
+    if (!h || !out10 || step < 0 || step >= (int)h->steps.size()) return LWOP_ERR_INVALID;
+    const Step &st = h->steps[step];
+    const LayerSpec &l = kLayers[st.layer];
+    out10[0] = st.layer;
+    out10[1] = st.is_dw ? 1 : 0;
+    out10[2] = st.H;
+    out10[3] = st.W;
+    out10[4] = st.is_dw ? l.cin : (st.layer == 0 ? 3 : l.cin);
+    out10[5] = st.is_dw ? l.cin : l.cout;
+    out10[6] = st.is_dw ? 3 : l.k;
+    out10[7] = (st.is_dw || st.layer == 0) ? l.stride : 1;
+    out10[8] = (st.is_dw || l.kind == L_CONV) ? l.dil : 1;
+    out10[9] = step_uses_gemm(st) ? 1 : 0;
+    return LWOP_OK;
+}
+
+int lwop_profile_forward(lwop_handle *h, const float *in_dev, int batch, int mode, float *heat_dev, float *paf_dev,
+                         float *step_ms, void *stream) {
+    if (!h || !in_dev || !heat_dev || !paf_dev || !step_ms) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (!h->has_weights) return fail(h, LWOP_ERR_NO_WEIGHTS, "lwop_profile_forward before lwop_load_weights");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_arena(h, mode);
+    if (rc != LWOP_OK) return rc;
+    const size_t n = h->steps.size();
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto &e : ev) CU_OK(h, cudaEventCreate(&e));
+    FwdIO io{in_dev, 0, heat_dev, paf_dev, nullptr, nullptr};
+    rc = run_forward(h, batch, mode, io, s, ev.data());
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == LWOP_OK && e != cudaSuccess) rc = fail(h, LWOP_ERR_CUDA, std::string("profile forward: ") + cudaGetErrorString(e));
+    if (rc == LWOP_OK)
+        for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&step_ms[i], ev[2 * i], ev[2 * i + 1]);
+    for (auto &e2 : ev) cudaEventDestroy(e2);
+    return rc;
 }
 
 long long lwop_launch_count(const lwop_handle *h, int reset) {

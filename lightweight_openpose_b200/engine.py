@@ -261,6 +261,28 @@ class Engine:
             return res, heat_h.numpy(), paf_h.numpy()
         return res
 
+    def step_descs(self):
+        """[(layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, uses_tcgen05), ...]"""
+        n = self.lib.lwop_num_steps(self.handle)
+        out = []
+        buf = (C.c_int * 10)()
+        for i in range(n):
+            _lib.check(self.lib.lwop_step_desc(self.handle, i, buf), self.handle)
+            out.append(tuple(int(v) for v in buf))
+        return out
+
+    def profile_forward(self, images, mode: str = "bf16"):
+        """One eager (graph-less) forward with CUDA events around every kernel; returns the per-step ms."""
+        torch = _torch()
+        B = images.shape[0]
+        heat = torch.empty((B, self.map_h, self.map_w, _lib.NUM_JOINTS), dtype=torch.float32, device=images.device)
+        paf = torch.empty((B, self.map_h, self.map_w, _lib.NUM_PAFS), dtype=torch.float32, device=images.device)
+        n = self.lib.lwop_num_steps(self.handle)
+        ms = (C.c_float * n)()
+        _lib.check(self.lib.lwop_profile_forward(self.handle, images.data_ptr(), B, _MODES[mode], heat.data_ptr(),
+                                                 paf.data_ptr(), ms, self._stream()), self.handle)
+        return [float(v) for v in ms]
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.lwop_launch_count(self.handle, int(reset)))
 
