@@ -237,6 +237,23 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     joints_per_img = float(np.mean([r.counts[0] for r in res]))
     persons_per_img = float(np.mean([r.counts[1] for r in res]))
 
+    if args.chunk > 0:
+        eng.set_option("chunk", args.chunk)
+    sweep = {}
+    if args.sweep_chunks and rank == 0:
+        for c in (32, 64, 128, 256):
+            if c > batch:
+                continue
+            eng.set_option("chunk", c)
+            for _ in range(2):
+                eng.infer_host(x_host, mode=args.mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                eng.infer_host(x_host, mode=args.mode)
+            torch.cuda.synchronize()
+            sweep[c] = round(1e3 * (time.perf_counter() - t0) / 5, 3)
+        eng.set_option("chunk", args.chunk if args.chunk > 0 else 64)
     # ---- end to end through the host-buffer C entry (lwop_infer_host) ----
     for _ in range(max(1, min(args.warmup, 3))):
         eng.infer_host(x_host, mode=args.mode)
@@ -311,6 +328,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                             "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 2),
                             "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)}
         fwd_ms = float(acc.sum())
+        if args.dump_steps:
+            with open(args.dump_steps, "w") as fh:
+                for d, ms in zip(descs, acc):
+                    fl, by = step_work(d, batch)
+                    fh.write(json.dumps({"layer": d[0], "kind": classify_step(d), "in_hw": [d[2], d[3]], "cin": d[4],
+                                         "cout": d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
+                                         "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
+                                         "gbs": round(by / (ms * 1e-3) / 1e9, 1)}) + "\n")
 
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 contract; cheap enough to always run) ----
         cpu = None
@@ -341,6 +366,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "e2e_uint8_frames": {"value": total_images / (e2e_u8_ms * 1e-3), "unit": "images/s",
                                      "h2d_bytes_per_step": int(u8_host.numel())},
                 "e2e_wall_ms_per_step": e2e_wall_ms / args.steps,
+                "e2e_chunk_sweep_ms": sweep or None,
             },
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -365,6 +391,9 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
     ap.add_argument("--cpu-images", type=int, default=16, help="frames in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage of the host-buffer path (0 = library default)")
+    ap.add_argument("--sweep-chunks", action="store_true", help="also time the host-buffer path for several chunk sizes")
+    ap.add_argument("--dump-steps", default=None, help="write per-kernel timings (one JSON object per line) here")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

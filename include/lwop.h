@@ -151,10 +151,16 @@ int lwop_decode_fetch(lwop_handle *h, const lwop_decode_tables *tables_dev, int 
  * per frame, batched): H2D of the frames, forward, decode, D2H of the compacted
  * result tables.  images_host: [batch,H,W,3] float32 (or uint8 when is_u8).
  * heat_host / paf_host may be NULL when the maps themselves are not wanted.
+ * The batch flows through a two-slot pipeline in chunks ("chunk" option): a
+ * private copy stream uploads chunk k+1 while `stream` computes chunk k, so with
+ * pinned host memory the PCIe transfer hides behind the kernels.
  * Synchronises `stream` before returning. */
 int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode,
                     float thre1, double thre2, const lwop_packed_tables *out_host,
                     float *heat_host, float *paf_host, void *stream);
+
+/* Tunables: "chunk" = images per pipeline stage of lwop_infer_host (default 64). */
+int lwop_set_option(lwop_handle *h, const char *name, long long value);
 
 /* ---- per-op entries mirroring src/net_factory.py (unit tests, eager mode) ---- */
 

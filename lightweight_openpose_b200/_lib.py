@@ -64,6 +64,7 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_same_out": (_i, [_i, _i]),
     "lwop_crc32c": (C.c_uint32, [_vp, _sz]),
     "lwop_launch_count": (C.c_longlong, [_vp, _i]),
+    "lwop_set_option": (_i, [_vp, C.c_char_p, C.c_longlong]),
     "lwop_num_steps": (_i, [_vp]),
     "lwop_step_desc": (_i, [_vp, _i, C.POINTER(_i)]),
     "lwop_profile_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.POINTER(_f), _vp]),

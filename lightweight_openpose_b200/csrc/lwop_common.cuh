@@ -34,6 +34,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Epilogue activation of the tensor-core kernels: ELU through ex2.approx with a cubic Taylor branch
+// near zero (exp(v)-1 by subtraction loses everything below ~1e-7 there).  Error <= ~3e-7 absolute,
+// far below the bf16 rounding of the stored value; the fp32 check path keeps expm1f.
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+    if (act == LWOP_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == LWOP_ACT_ELU) {
+        const float small = v * (1.0f + v * (0.5f + v * (1.0f / 6.0f)));
+        const float big = __expf(v) - 1.0f;
+        const float neg = v > -0.0625f ? small : big;
+        return v > 0.0f ? v : neg;
+    }
+    return v;
+}
+
 // element load/store as float for the two storage types
 __device__ __forceinline__ float ld_as_float(const float *p) { return *p; }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
@@ -124,6 +138,18 @@ __device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, const void *d
         : "memory");
 }
 
+// 2D tiled store smem -> global (bulk async group), coordinates (c0 = innermost, c1)
+__device__ __forceinline__ void tma_store_2d(const void *desc, const void *smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed bulk groups have completed
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tcgen05 ----
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -162,6 +188,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
 }

@@ -41,6 +41,7 @@ struct GemmParams {
     int ldo, out_col0, ldr;
     int out_is_f32, act;
     int num_m_tiles, num_n_tiles;
+    int use_tma_store;              // wide bf16 output through shared-memory staging + TMA store
 };
 
 template <int BLOCK_N, int KSWZ, int STAGES>
@@ -50,13 +51,16 @@ struct SmemLayout {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kBiasOffset = kBarOffset + 256;
-    static constexpr int kTotal = kBiasOffset + 512 * 4 + 1024;   // + alignment slack
+    // epilogue staging for TMA stores: 4 warps x (32 rows x 128 B), 1024-byte aligned (128B swizzle)
+    static constexpr int kStagingOffset = ((kBiasOffset + 512 * 4 + 1023) / 1024) * 1024;
+    static constexpr int kStagingBytes = BLOCK_N >= 64 ? 4 * 4096 : 0;
+    static constexpr int kTotal = kStagingOffset + kStagingBytes + 1024;   // + alignment slack
 };
 
 template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
     using L = SmemLayout<BLOCK_N, KSWZ, STAGES>;
     constexpr int BLOCK_K = KSWZ / 2;                 // bf16 elements per swizzle row
     constexpr int kMmasPerBlock = BLOCK_K / 16;
@@ -81,6 +85,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (p.use_tma_store) tma_prefetch_desc(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -172,6 +177,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool narrow = (p.Cout != p.Cout_pad) || p.out_is_f32 || (p.out_col0 & 7) || (p.ldo & 7);
+        unsigned char *stg = smem + L::kStagingOffset + q * 4096;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
             const long long m = (long long)m_tile * kBlockM + q * 32 + lane;
@@ -180,6 +186,55 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             const bool row_ok = m < p.M;
+            if (BLOCK_N >= 64 && p.use_tma_store) {
+                // ---- wide bf16 output: 64 columns at a time -> swizzled staging -> one TMA store per warp ----
+#pragma unroll 1
+                for (int g = 0; g < BLOCK_N / 64; ++g) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64), r0);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + 32), r1);
+                    tmem_ld_wait();
+                    if (g == BLOCK_N / 64 - 1) {             // accumulator drained: hand it back to the MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (lane == 0) bulk_wait_read_all();     // previous store has finished reading the staging tile
+                    __syncwarp();
+                    const float *bs = bias_s + n0 + g * 64;
+                    const uint4 *rp = (p.residual && row_ok)
+                                          ? reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + n0 + g * 64)
+                                          : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {            // 8 columns = one 16-byte chunk
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = j * 8 + e;
+                            const uint32_t raw = c < 32 ? r0[c] : r1[c - 32];
+                            v[e] = apply_act_fast(__uint_as_float(raw) + bs[c], p.act);
+                        }
+                        if (rp) {
+                            const uint4 rr = rp[j];
+                            v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                            v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                        *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_out, stg, p.out_col0 + n0 + g * 64, m_tile * kBlockM + q * 32);
+                        bulk_commit_group();
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N; c += 16) {
                 uint32_t r[16];
@@ -187,7 +242,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_s[n0 + c + j], p.act);
+                for (int j = 0; j < 16; ++j) v[j] = apply_act_fast(__uint_as_float(r[j]) + bias_s[n0 + c + j], p.act);
                 if (row_ok) {
                     if (p.residual) {
                         const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + n0 + c);
@@ -228,6 +283,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();                      // outstanding TMA stores complete before exit
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -278,8 +334,27 @@ bool gemm_driver_ready(char *err, size_t errlen) {
     return true;
 }
 
+int gemm_num_sms() { return g_num_sms; }
+
+bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,
+                       const cuuint64_t *strides_bytes, const cuuint32_t *box, int swizzle_bytes, char *err,
+                       size_t errlen) {
+    if (!gemm_driver_ready(err, errlen)) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                                strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled (rank %d) failed: CUresult %d", rank, (int)r);
+        return false;
+    }
+    return true;
+}
+
 struct GemmPlan {
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_out;
     GemmParams p;
     int block_n, kswz, im2col, stages;
     int grid;
@@ -298,7 +373,8 @@ cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, flo
     GemmParams p = pl->p;
     if (out_override) p.out = out_override;
     if (out2_override) p.out2 = out2_override;
-    kfn<<<pl->grid, kNumThreads, smem, s>>>(pl->map_a, pl->map_b, p);
+    if (out_override) p.use_tma_store = 0;         // the store map is bound to the plan's own output
+    kfn<<<pl->grid, kNumThreads, smem, s>>>(pl->map_a, pl->map_b, pl->map_out, p);
     return cudaGetLastError();
 }
 
@@ -430,6 +506,27 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
             free(pl);
             return nullptr;
         }
+    }
+    // wide bf16 outputs leave through shared-memory staging + TMA store (full 128-byte lines)
+    const bool wide = d.out_dtype == LWOP_DT_BF16 && d.Cout == d.Cout_pad && (d.out_col0 % 8) == 0 &&
+                      (d.ldo % 8) == 0 && block_n >= 64 && d.out != nullptr && !getenv("LWOP_NO_TMA_STORE");
+    p.use_tma_store = 0;
+    if (wide) {
+        cuuint64_t dims[2] = {(cuuint64_t)d.ldo, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)d.ldo * 2};
+        cuuint32_t box[2] = {64, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encode_tiled(&pl->map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(err, errlen, "tensor map (out) encode failed: CUresult %d", (int)r);
+            free(pl);
+            return nullptr;
+        }
+        p.use_tma_store = 1;
+    } else {
+        pl->map_out = pl->map_b;       // unused, but must be a valid descriptor for the prefetch-free path
     }
     return pl;
 }

@@ -61,6 +61,18 @@ void gemm_plan_destroy(GemmPlan *p);
 cudaError_t gemm_plan_launch(const GemmPlan *p, cudaStream_t s, void *out_override = nullptr,
                              float *out2_override = nullptr);
 bool gemm_driver_ready(char *err, size_t errlen);
+int gemm_num_sms();
+// cuTensorMapEncodeTiled for a bf16 tensor (rank 2..4), no interleave, zero OOB fill
+bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,
+                       const cuuint64_t *strides_bytes, const cuuint32_t *box, int swizzle_bytes, char *err,
+                       size_t errlen);
+
+// lwop_dw.cu -- TMA-staged depthwise 3x3
+struct DwPlan;
+bool dw_plan_supported(int C, int stride, int dil);
+DwPlan *dw_plan_create(const DwArgs &a, char *err, size_t errlen);
+void dw_plan_destroy(DwPlan *p);
+cudaError_t dw_plan_launch(const DwPlan *p, cudaStream_t s);
 
 // lwop_decode.cu
 struct DecodeArgs {

@@ -86,6 +86,7 @@ int pad_cin(int c) { return c == 40 ? 64 : c; }
 
 struct PlanSet {
     std::vector<GemmPlan *> plans;   // per step (nullptr for non-GEMM steps)
+    std::vector<DwPlan *> dw;        // per step (nullptr for non-depthwise steps)
 };
 
 struct GraphEntry {
@@ -118,7 +119,7 @@ struct lwop_handle {
     void *arena_bf16[NUM_BUF] = {};
     void *arena_f32[NUM_BUF] = {};
     std::map<int, PlanSet> plan_sets;            // by batch
-    std::map<long long, GraphEntry> graphs;      // by batch * 8 + mode
+    std::map<long long, std::vector<GraphEntry>> graphs;   // by batch * 8 + mode; entries differ in I/O pointers
 
     // decode scratch
     float *peaks = nullptr;
@@ -129,10 +130,13 @@ struct lwop_handle {
     float *pk_keypoints = nullptr;
     size_t pk_joints_cap = 0, pk_limbs_cap = 0, pk_persons_cap = 0;
     int *h_offsets = nullptr;                    // pinned
-    // infer_host staging
-    void *stage_in = nullptr;
-    size_t stage_in_bytes = 0;
-    float *stage_heat = nullptr, *stage_paf = nullptr;
+    // infer_host pipeline: two slots (input staging + maps), a copy stream and events
+    int chunk = 0, pipe_chunk = 0;
+    bool pipe_ready = false;
+    void *slot_in[2] = {};
+    float *slot_heat[2] = {}, *slot_paf[2] = {};
+    cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_done[2] = {}, ev_start = nullptr, ev_join = nullptr;
+    cudaStream_t copy_stream = nullptr, decode_stream = nullptr;
     lwop_decode_tables own_tables = {};
     int own_tables_batch = 0;
 };
@@ -246,12 +250,23 @@ int ensure_arena(lwop_handle *h, int mode) {
 }
 
 void destroy_plans(lwop_handle *h) {
-    for (auto &kv : h->plan_sets)
+    for (auto &kv : h->plan_sets) {
         for (GemmPlan *p : kv.second.plans)
             if (p) gemm_plan_destroy(p);
+        for (DwPlan *p : kv.second.dw)
+            if (p) dw_plan_destroy(p);
+    }
     h->plan_sets.clear();
     for (auto &kv : h->graphs)
-        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        for (auto &g : kv.second)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+void destroy_graphs_only(lwop_handle *h) {
+    for (auto &kv : h->graphs)
+        for (auto &g : kv.second)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
 }
 
@@ -265,11 +280,30 @@ int get_plans(lwop_handle *h, int batch, PlanSet **out) {
     }
     PlanSet ps;
     ps.plans.assign(h->steps.size(), nullptr);
+    ps.dw.assign(h->steps.size(), nullptr);
     char err[256];
+    auto cleanup = [&]() {
+        for (GemmPlan *p : ps.plans)
+            if (p) gemm_plan_destroy(p);
+        for (DwPlan *p : ps.dw)
+            if (p) dw_plan_destroy(p);
+    };
     for (size_t i = 0; i < h->steps.size(); ++i) {
         const Step &s = h->steps[i];
-        if (!step_uses_gemm(s)) continue;
         const LayerSpec &l = kLayers[s.layer];
+        if (s.is_dw) {
+            DwArgs a{};
+            a.in = h->arena_bf16[s.in]; a.out = h->arena_bf16[s.out]; a.dtype = LWOP_DT_BF16;
+            a.w = h->blob + h->off_dw[s.layer];
+            a.B = batch; a.H = s.H; a.W = s.W; a.C = l.cin; a.stride = l.stride; a.dil = l.dil;
+            ps.dw[i] = dw_plan_create(a, err, sizeof(err));
+            if (!ps.dw[i]) {
+                cleanup();
+                return fail(h, LWOP_ERR_UNSUPPORTED, std::string("layer ") + std::to_string(s.layer) + " (dw): " + err);
+            }
+            continue;
+        }
+        if (!step_uses_gemm(s)) continue;
         GemmConvDesc d{};
         d.in = h->arena_bf16[s.in];
         d.w_packed = h->w_bf16[s.layer];
@@ -293,8 +327,7 @@ int get_plans(lwop_handle *h, int batch, PlanSet **out) {
         d.ldr = 128;
         ps.plans[i] = gemm_plan_create(d, err, sizeof(err));
         if (!ps.plans[i]) {
-            for (GemmPlan *p : ps.plans)
-                if (p) gemm_plan_destroy(p);
+            cleanup();
             return fail(h, LWOP_ERR_UNSUPPORTED, std::string("layer ") + std::to_string(s.layer) + ": " + err);
         }
     }
@@ -363,6 +396,7 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
             a.in = in; a.out = out; a.dtype = dt; a.w = h->blob + h->off_dw[st.layer];
             a.B = batch; a.H = st.H; a.W = st.W; a.C = l.cin; a.stride = l.stride; a.dil = l.dil;
             if (f32) CU_OK(h, launch_depthwise_simple(a, s));
+            else if (mode == LWOP_MODE_BF16) CU_OK(h, dw_plan_launch(ps->dw[i], s));
             else CU_OK(h, launch_depthwise_bf16(a, s));
             h->launches++;
             continue;
@@ -406,13 +440,18 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
     if (!use_graph) return run_forward(h, batch, mode, io, s);
 
     const long long key = (long long)batch * 8 + mode;
-    GraphEntry &g = h->graphs[key];
-    const bool same = g.exec && g.in == io.in && g.heat == io.heat && g.paf == io.paf && g.h1 == io.h1 &&
-                      g.p1 == io.p1 && g.in_u8 == io.in_u8;
-    if (!same) {
-        if (g.exec) {
-            cudaGraphExecDestroy(g.exec);
-            g.exec = nullptr;
+    std::vector<GraphEntry> &cache = h->graphs[key];
+    GraphEntry *gp = nullptr;
+    for (auto &c : cache)
+        if (c.exec && c.in == io.in && c.heat == io.heat && c.paf == io.paf && c.h1 == io.h1 && c.p1 == io.p1 &&
+            c.in_u8 == io.in_u8) {
+            gp = &c;
+            break;
+        }
+    if (!gp) {
+        if (cache.size() >= 8) {            // callers cycling through many buffers: drop the oldest graph
+            if (cache.front().exec) cudaGraphExecDestroy(cache.front().exec);
+            cache.erase(cache.begin());
         }
         // One eager pass first: creates the plans (tensor-map encoding calls the driver), sets the
         // per-kernel shared-memory attributes and surfaces launch errors outside of stream capture.
@@ -435,12 +474,16 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
             if (rc != LWOP_OK) return rc;
             return fail(h, LWOP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
         }
-        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        GraphEntry ne;
+        e = cudaGraphInstantiate(&ne.exec, graph, 0);
         cudaGraphDestroy(graph);
         cudaStreamDestroy(cs);
         if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        g.in = io.in; g.heat = io.heat; g.paf = io.paf; g.h1 = io.h1; g.p1 = io.p1; g.in_u8 = io.in_u8;
+        ne.in = io.in; ne.heat = io.heat; ne.paf = io.paf; ne.h1 = io.h1; ne.p1 = io.p1; ne.in_u8 = io.in_u8;
+        cache.push_back(ne);
+        gp = &cache.back();
     }
+    GraphEntry &g = *gp;
     CU_OK(h, cudaGraphLaunch(g.exec, s));
     h->launches += (long long)h->steps.size();
     return LWOP_OK;
@@ -588,9 +631,18 @@ int lwop_destroy(lwop_handle *h) {
     if (h->pk_limbs) cudaFree(h->pk_limbs);
     if (h->pk_persons) cudaFree(h->pk_persons);
     if (h->pk_keypoints) cudaFree(h->pk_keypoints);
-    if (h->stage_in) cudaFree(h->stage_in);
-    if (h->stage_heat) cudaFree(h->stage_heat);
-    if (h->stage_paf) cudaFree(h->stage_paf);
+    for (int k = 0; k < 2; ++k) {
+        if (h->slot_in[k]) cudaFree(h->slot_in[k]);
+        if (h->slot_heat[k]) cudaFree(h->slot_heat[k]);
+        if (h->slot_paf[k]) cudaFree(h->slot_paf[k]);
+        if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
+        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+        if (h->ev_fwd[k]) cudaEventDestroy(h->ev_fwd[k]);
+    }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->decode_stream) cudaStreamDestroy(h->decode_stream);
     if (h->own_tables.counts) cudaFree(h->own_tables.counts);
     if (h->own_tables.joints) cudaFree(h->own_tables.joints);
     if (h->own_tables.limbs) cudaFree(h->own_tables.limbs);
@@ -719,33 +771,95 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
     if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
     cudaStream_t s = (cudaStream_t)stream;
     CU_OK(h, cudaSetDevice(h->device));
-    const size_t in_bytes = (size_t)batch * h->H * h->W * 3 * (is_u8 ? 1 : 4);
-    const size_t cap_bytes = (size_t)h->max_batch * h->H * h->W * 3 * 4;
-    if (!h->stage_in) {
-        CU_OK(h, cudaMalloc(&h->stage_in, cap_bytes));
-        h->stage_in_bytes = cap_bytes;
-    }
+    // The batch is cut into chunks that flow through a two-slot pipeline: the copy stream uploads chunk
+    // k+1 while the compute stream runs forward + decode of chunk k (one CUDA graph per slot).
+    int chunk = h->chunk > 0 ? h->chunk : 64;
+    if (chunk > batch) chunk = batch;
+    if (chunk > h->max_batch) chunk = h->max_batch;
+    const size_t img_elems = (size_t)h->H * h->W * 3;
     const size_t px = (size_t)h->h8 * h->w8;
-    if (!h->stage_heat) {
-        CU_OK(h, cudaMalloc(&h->stage_heat, (size_t)h->max_batch * px * LWOP_NUM_JOINTS * 4));
-        CU_OK(h, cudaMalloc(&h->stage_paf, (size_t)h->max_batch * px * LWOP_NUM_PAFS * 4));
+    if (!h->pipe_ready || h->pipe_chunk < chunk) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->slot_in[k]) cudaFree(h->slot_in[k]);
+            if (h->slot_heat[k]) cudaFree(h->slot_heat[k]);
+            if (h->slot_paf[k]) cudaFree(h->slot_paf[k]);
+            CU_OK(h, cudaMalloc(&h->slot_in[k], (size_t)chunk * img_elems * 4));
+            CU_OK(h, cudaMalloc(&h->slot_heat[k], (size_t)chunk * px * LWOP_NUM_JOINTS * 4));
+            CU_OK(h, cudaMalloc(&h->slot_paf[k], (size_t)chunk * px * LWOP_NUM_PAFS * 4));
+            if (!h->ev_h2d[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
+            if (!h->ev_done[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+            if (!h->ev_fwd[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_fwd[k], cudaEventDisableTiming));
+        }
+        if (!h->ev_start) CU_OK(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        if (!h->ev_join) CU_OK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        if (!h->copy_stream) CU_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->decode_stream) CU_OK(h, cudaStreamCreateWithFlags(&h->decode_stream, cudaStreamNonBlocking));
+        h->pipe_chunk = chunk;
+        h->pipe_ready = true;
+        destroy_graphs_only(h);          // slot pointers changed
     }
     int rc = ensure_own_tables(h);
     if (rc != LWOP_OK) return rc;
-    CU_OK(h, cudaMemcpyAsync(h->stage_in, images_host, in_bytes, cudaMemcpyHostToDevice, s));
-    FwdIO io{h->stage_in, is_u8, h->stage_heat, h->stage_paf, nullptr, nullptr};
-    rc = forward_impl(h, io, batch, mode, s);
+    rc = ensure_decode_scratch(h);
     if (rc != LWOP_OK) return rc;
-    rc = lwop_decode(h, h->stage_heat, h->stage_paf, batch, h->h8, h->w8, h->H, h->W, thre1, thre2, &h->own_tables,
-                     stream);
-    if (rc != LWOP_OK) return rc;
-    if (heat_host)
-        CU_OK(h, cudaMemcpyAsync(heat_host, h->stage_heat, (size_t)batch * px * LWOP_NUM_JOINTS * 4,
-                                 cudaMemcpyDeviceToHost, s));
-    if (paf_host)
-        CU_OK(h, cudaMemcpyAsync(paf_host, h->stage_paf, (size_t)batch * px * LWOP_NUM_PAFS * 4,
-                                 cudaMemcpyDeviceToHost, s));
+    const size_t esz = is_u8 ? 1 : 4;
+    // three streams: copy (H2D), `s` (forward), decode.  Slot k&1 holds chunk k's frames and maps; it is
+    // re-used by chunk k+2 once chunk k's decode (and optional map download) has finished.
+    cudaStream_t ds = h->decode_stream;
+    CU_OK(h, cudaEventRecord(h->ev_start, s));
+    CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
+    CU_OK(h, cudaStreamWaitEvent(ds, h->ev_start, 0));
+    int k = 0;
+    for (int b0 = 0; b0 < batch; b0 += chunk, ++k) {
+        const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const int slot = k & 1;
+        if (k >= 2) {
+            CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_fwd[slot], 0));   // frames of chunk k-2 consumed
+            CU_OK(h, cudaStreamWaitEvent(s, h->ev_done[slot], 0));               // maps of chunk k-2 decoded
+        }
+        CU_OK(h, cudaMemcpyAsync(h->slot_in[slot], (const char *)images_host + (size_t)b0 * img_elems * esz,
+                                 (size_t)nb * img_elems * esz, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        CU_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+        FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr};
+        rc = forward_impl(h, io, nb, mode, s);
+        if (rc != LWOP_OK) return rc;
+        CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
+        CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
+        lwop_decode_tables t = h->own_tables;
+        t.counts += (size_t)b0 * LWOP_COUNTS;
+        t.joints += (size_t)b0 * LWOP_MAX_JOINTS * 6;
+        t.limbs += (size_t)b0 * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 5;
+        t.persons += (size_t)b0 * LWOP_MAX_PERSONS * 16;
+        t.keypoints += (size_t)b0 * LWOP_MAX_PERSONS * 42;
+        DecodeArgs a{};
+        a.heat = h->slot_heat[slot]; a.paf = h->slot_paf[slot]; a.B = nb; a.h = h->h8; a.w = h->w8; a.H = h->H; a.W = h->W;
+        a.thre1 = thre1; a.thre2 = thre2; a.t = t;
+        a.peaks = h->peaks + (size_t)b0 * LWOP_NUM_JOINTS * LWOP_MAX_PEAKS * 4;
+        a.peak_counts = h->peak_counts + (size_t)b0 * 16;
+        a.work = h->group_work + (size_t)b0 * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 16;
+        CU_OK(h, launch_decode(a, ds, &h->launches));
+        if (heat_host)
+            CU_OK(h, cudaMemcpyAsync(heat_host + (size_t)b0 * px * LWOP_NUM_JOINTS, h->slot_heat[slot],
+                                     (size_t)nb * px * LWOP_NUM_JOINTS * 4, cudaMemcpyDeviceToHost, ds));
+        if (paf_host)
+            CU_OK(h, cudaMemcpyAsync(paf_host + (size_t)b0 * px * LWOP_NUM_PAFS, h->slot_paf[slot],
+                                     (size_t)nb * px * LWOP_NUM_PAFS * 4, cudaMemcpyDeviceToHost, ds));
+        CU_OK(h, cudaEventRecord(h->ev_done[slot], ds));
+    }
+    CU_OK(h, cudaEventRecord(h->ev_join, ds));
+    CU_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     return lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
+}
+
+int lwop_set_option(lwop_handle *h, const char *name, long long value) {
+    if (!h || !name) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (strcmp(name, "chunk") == 0) {
+        if (value < 1) return fail(h, LWOP_ERR_INVALID, "chunk must be >= 1");
+        h->chunk = (int)value;
+        return LWOP_OK;
+    }
+    return fail(h, LWOP_ERR_INVALID, std::string("unknown option ") + name);
 }
 
 int lwop_conv2d(lwop_handle *h, int mode, const void *in_dev, int in_dtype, int batch, int height, int width, int cin,
@@ -810,7 +924,14 @@ int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype, i
     DwArgs a{};
     a.in = in_dev; a.out = out_dev; a.dtype = dtype; a.w = w_dev;
     a.B = batch; a.H = height; a.W = width; a.C = channels; a.stride = stride; a.dil = dilation;
-    if (mode == LWOP_MODE_BF16 && dtype == LWOP_DT_BF16) {
+    if (mode == LWOP_MODE_BF16 && dtype == LWOP_DT_BF16 && dw_plan_supported(channels, stride, dilation)) {
+        char err[256];
+        DwPlan *pl = dw_plan_create(a, err, sizeof(err));
+        if (!pl) return fail(h, LWOP_ERR_UNSUPPORTED, err);
+        cudaError_t e = dw_plan_launch(pl, (cudaStream_t)stream);
+        dw_plan_destroy(pl);      // the tensor map is a by-value kernel argument
+        if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("depthwise launch: ") + cudaGetErrorString(e));
+    } else if ((mode == LWOP_MODE_BF16 || mode == LWOP_MODE_BF16_DIRECT) && dtype == LWOP_DT_BF16) {
         if (channels % 8 != 0 || !((stride == 1 && dilation <= 2) || (stride == 2 && dilation == 1)))
             return fail(h, LWOP_ERR_UNSUPPORTED, "vector depthwise needs C % 8 == 0 and (s1,d1|d2) or (s2,d1)");
         CU_OK(h, launch_depthwise_bf16(a, (cudaStream_t)stream));

@@ -85,6 +85,7 @@ class Engine:
         self.weights_source: Optional[str] = None
         self._tables = None
         self._host = None
+        self._out = {}
 
     def close(self) -> None:
         if getattr(self, "handle", None):
@@ -117,16 +118,16 @@ class Engine:
 
     def forward(self, images, mode: str = "bf16", return_stage1: bool = False):
         """images: CUDA tensor [B,H,W,3] float32 in [0,1] or uint8.  Returns
-        ``(heat [B,h,w,14], paf [B,h,w,26])`` float32 CUDA tensors (+ stage-1 maps)."""
+        ``(heat [B,h,w,14], paf [B,h,w,26])`` float32 CUDA tensors (+ stage-1 maps).
+        The returned tensors are engine-owned and reused by the next call with the
+        same batch size."""
         torch = _torch()
         if images.device.type != "cuda" or not images.is_contiguous():
             raise ValueError("images must be a contiguous CUDA tensor")
         B, H, W, Cc = images.shape
         if (H, W, Cc) != (self.height, self.width, 3) or B > self.max_batch:
             raise ValueError(f"engine built for [<= {self.max_batch},{self.height},{self.width},3], got {tuple(images.shape)}")
-        dev = images.device
-        heat = torch.empty((B, self.map_h, self.map_w, _lib.NUM_JOINTS), dtype=torch.float32, device=dev)
-        paf = torch.empty((B, self.map_h, self.map_w, _lib.NUM_PAFS), dtype=torch.float32, device=dev)
+        heat, paf, h1, p1 = self._outputs(B, images.device)
         m = _MODES[mode]
         if images.dtype == torch.uint8:
             if return_stage1:
@@ -137,14 +138,26 @@ class Engine:
         if images.dtype != torch.float32:
             raise ValueError("images must be float32 or uint8")
         if return_stage1:
-            h1 = torch.empty_like(heat)
-            p1 = torch.empty_like(paf)
             _lib.check(self.lib.lwop_forward(self.handle, images.data_ptr(), B, m, heat.data_ptr(), paf.data_ptr(),
                                              h1.data_ptr(), p1.data_ptr(), self._stream()), self.handle)
             return heat, paf, h1, p1
         _lib.check(self.lib.lwop_forward(self.handle, images.data_ptr(), B, m, heat.data_ptr(), paf.data_ptr(),
                                          None, None, self._stream()), self.handle)
         return heat, paf
+
+    def _outputs(self, batch: int, dev):
+        """Engine-owned output maps per batch size (stable pointers keep the CUDA graph
+        valid across calls).  They are overwritten by the next forward of the same
+        batch size: clone what must outlive it."""
+        torch = _torch()
+        bufs = self._out.get(batch)
+        if bufs is None:
+            shape_h = (batch, self.map_h, self.map_w, _lib.NUM_JOINTS)
+            shape_p = (batch, self.map_h, self.map_w, _lib.NUM_PAFS)
+            bufs = (torch.empty(shape_h, dtype=torch.float32, device=dev), torch.empty(shape_p, dtype=torch.float32, device=dev),
+                    torch.empty(shape_h, dtype=torch.float32, device=dev), torch.empty(shape_p, dtype=torch.float32, device=dev))
+            self._out[batch] = bufs
+        return bufs
 
     # -- decode ------------------------------------------------------------------
     def _device_tables(self):
@@ -282,6 +295,9 @@ class Engine:
         _lib.check(self.lib.lwop_profile_forward(self.handle, images.data_ptr(), B, _MODES[mode], heat.data_ptr(),
                                                  paf.data_ptr(), ms, self._stream()), self.handle)
         return [float(v) for v in ms]
+
+    def set_option(self, name: str, value: int) -> None:
+        _lib.check(self.lib.lwop_set_option(self.handle, name.encode(), int(value)), self.handle)
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.lwop_launch_count(self.handle, int(reset)))

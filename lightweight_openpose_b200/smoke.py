@@ -24,7 +24,7 @@ def run(verbose: bool = True) -> None:
     eng.load_variables(variables, source)
     x = synth.synth_batch([0, 1], H, W)
     xd = torch.from_numpy(x).cuda()
-    heat, paf = eng.forward(xd, mode="bf16")
+    heat, paf = (t.clone() for t in eng.forward(xd, mode="bf16"))
     heat32, paf32 = eng.forward(xd, mode="fp32")
     torch.cuda.synchronize()
     oh, op = ForwardOracle(variables)(x)

@@ -113,7 +113,7 @@ def lightweight_openpose(inputs, num_joints, num_pafs, is_training=True, *, retu
         outs = tuple(o.to(torch.float32) for o in outs)
     else:
         eng = engine.get_engine(H, W, B, dev_index)
-        outs = eng.forward(x, mode=mode, return_stage1=return_stage1)
+        outs = tuple(o.clone() for o in eng.forward(x, mode=mode, return_stage1=return_stage1))
     outs = outs if return_stage1 else outs[:2]
     if was_numpy:
         outs = tuple(o.cpu().numpy() for o in outs)

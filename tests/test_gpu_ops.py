@@ -124,19 +124,22 @@ DW_CASES = [
 
 
 @pytest.mark.parametrize("case", DW_CASES)
-@pytest.mark.parametrize("vec", [True, False])
-def test_depthwise_kernels(eng, case, vec):
+@pytest.mark.parametrize("kind", ["tma", "vector", "fp32"])
+def test_depthwise_kernels(eng, case, kind):
     B, H, W, Cc, stride, dil = case
     rng = np.random.default_rng(11)
     x = bf16_round(rng.normal(size=(B, H, W, Cc)))
     w = (rng.normal(size=(9, Cc)) / 3.0).astype(np.float32)
     Ho, Wo = -(-H // stride), -(-W // stride)
     xd = torch.from_numpy(x).cuda()
+    vec = kind != "fp32"
     if vec:
         xd = xd.to(torch.bfloat16)
     out = torch.empty((B, Ho, Wo, Cc), dtype=xd.dtype, device="cuda")
-    rc = eng.lib.lwop_depthwise3x3(eng.handle, _lib.MODE_BF16 if vec else _lib.MODE_FP32_CHECK, xd.data_ptr(),
-                                   _lib.DT_BF16 if vec else _lib.DT_F32, B, H, W, Cc, torch.from_numpy(w).cuda().data_ptr(),
+    mode = {"tma": _lib.MODE_BF16, "vector": _lib.MODE_BF16_DIRECT, "fp32": _lib.MODE_FP32_CHECK}[kind]
+    wd = torch.from_numpy(w).cuda()
+    rc = eng.lib.lwop_depthwise3x3(eng.handle, mode, xd.data_ptr(),
+                                   _lib.DT_BF16 if vec else _lib.DT_F32, B, H, W, Cc, wd.data_ptr(),
                                    stride, dil, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, eng.handle)
     torch.cuda.synchronize()
