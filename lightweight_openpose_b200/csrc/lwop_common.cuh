@@ -61,6 +61,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// packed fp32 FMA (Blackwell FFMA2): two independent fused multiply-adds per instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05 (see /opt/skills/guides/blackwell_cuda_programming.md)
 // ---------------------------------------------------------------------------
@@ -117,6 +130,26 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *desc, ui
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// 2D tiled load multicast to every CTA of the cluster named in cta_mask: the box lands at the same
+// shared-memory offset in each of them and signals the barrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_multicast(void *smem_dst, const void *desc, uint64_t *bar, int c0,
+                                                      int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // 4D tiled load: coordinates (c, w, h, n)
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const void *desc, uint64_t *bar, int c0, int c1,
@@ -180,6 +213,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i = lane i)
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {

@@ -66,113 +66,91 @@ __device__ __forceinline__ int cv_round(double v) { return (int)rint(v); }
 // ---------------------------------------------------------------------------
 // K1: per (image, joint channel): threshold, greedy radius-5 NMS, refinement.
 // ---------------------------------------------------------------------------
+constexpr int kRefineMax = 64;      // separable refinement handles up-sampled patches up to 64 x 64
+
 __global__ void __launch_bounds__(256)
 peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor,
              float *__restrict__ peaks, int *__restrict__ peak_counts, int *__restrict__ counts) {
     extern __shared__ unsigned char smem_raw[];
     const int npix = h * w;
-    float *val = reinterpret_cast<float *>(smem_raw);
-    unsigned char *state = reinterpret_cast<unsigned char *>(val + npix);   // 0 none, 1 undecided, 2 kept, 3 dead
-    __shared__ int s_n;
-    __shared__ int s_list[LWOP_MAX_PEAKS * 4];      // kept pixel indices (unsorted, up to 4x cap before truncation)
-    __shared__ int s_sorted[LWOP_MAX_PEAKS];
+    float *val = reinterpret_cast<float *>(smem_raw);                 // the channel's map
+    int *cand = reinterpret_cast<int *>(val + npix);                  // candidate pixels; index < 0 = suppressed
+    __shared__ int s_nc, s_best_p, s_n;
+    __shared__ float s_wv[8];
+    __shared__ int s_wp[8];
+    __shared__ int s_kept[LWOP_MAX_PEAKS];
+    // per-warp scratch of the separable refinement: horizontal pass + tap tables
+    __shared__ float s_h[8][5][kRefineMax];
+    __shared__ float s_cx[8][kRefineMax][4], s_cy[8][kRefineMax][4];
+    __shared__ signed char s_sx[8][kRefineMax], s_sy[8][kRefineMax];
 
     const int ch = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const float *src = heat + (long long)b * npix * C + ch;
+    if (tid == 0) { s_nc = 0; s_n = 0; }
+    __syncthreads();
     for (int p = tid; p < npix; p += blockDim.x) {
         const float v = src[(long long)p * C];
         val[p] = v;
-        state[p] = v > thre1 ? 1 : 0;               // np.where(img > thre1), pose_decode.py:54
+        if (v > thre1) cand[atomicAdd(&s_nc, 1)] = p;               // np.where(img > thre1), pose_decode.py:54
     }
-    if (tid == 0) s_n = 0;
     __syncthreads();
+    const int nc = s_nc;
 
-    // Parallel form of the greedy loop (:62-70): in score order a pixel is kept
-    // iff no already-kept pixel lies within distance 5.  Round: every undecided
-    // pixel that beats all undecided pixels of its disk is kept; then undecided
-    // pixels inside a kept disk die.  Priority = (score, row-major index), larger
-    // first (exact ties: see DESIGN.md).
+    // The greedy loop of find_peaks_v2 (:62-70) verbatim: take the best remaining candidate, drop every
+    // remaining candidate within Euclidean distance 5 of it, repeat.  "Best" = larger score, exact ties
+    // towards the larger row-major index.  One block-wide arg-max per kept peak.
+    int n = 0;
     while (true) {
-        unsigned long long keep_mask = 0;
-        int undecided = 0;
-        int slot = 0;
-        for (int p = tid; p < npix; p += blockDim.x, ++slot) {
-            if (state[p] != 1) continue;
-            undecided = 1;
-            const int py = p / w, px = p - py * w;
+        float bv = -INFINITY;
+        int bp = -1;
+        for (int i = tid; i < nc; i += blockDim.x) {
+            const int p = cand[i];
+            if (p < 0) continue;
             const float v = val[p];
-            bool best = true;
-            for (int dy = -kRadius; dy <= kRadius && best; ++dy) {
-                const int qy = py + dy;
-                if (qy < 0 || qy >= h) continue;
-                for (int dx = -kRadius; dx <= kRadius; ++dx) {
-                    if (dx * dx + dy * dy > kRadius * kRadius || (dx == 0 && dy == 0)) continue;
-                    const int qx = px + dx;
-                    if (qx < 0 || qx >= w) continue;
-                    const int q = qy * w + qx;
-                    if (state[q] != 1) continue;
-                    const float u = val[q];
-                    if (u > v || (u == v && q > p)) { best = false; break; }
-                }
-            }
-            if (best) keep_mask |= 1ull << slot;
+            if (v > bv || (v == bv && p > bp)) { bv = v; bp = p; }
         }
-        if (!__syncthreads_or(undecided)) break;
-        slot = 0;
-        for (int p = tid; p < npix; p += blockDim.x, ++slot)
-            if (keep_mask >> slot & 1ull) state[p] = 2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (ov > bv || (ov == bv && op > bp)) { bv = ov; bp = op; }
+        }
+        if (lane == 0) { s_wv[warp] = bv; s_wp[warp] = bp; }
         __syncthreads();
-        for (int p = tid; p < npix; p += blockDim.x) {
-            if (state[p] != 1) continue;
+        if (tid == 0) {
+            float fv = s_wv[0];
+            int fp = s_wp[0];
+            for (int k = 1; k < nwarps; ++k)
+                if (s_wv[k] > fv || (s_wv[k] == fv && s_wp[k] > fp)) { fv = s_wv[k]; fp = s_wp[k]; }
+            s_best_p = fp;
+            if (fp >= 0 && n < LWOP_MAX_PEAKS) s_kept[n] = fp;
+        }
+        __syncthreads();
+        const int best = s_best_p;
+        if (best < 0) break;
+        if (n >= LWOP_MAX_PEAKS) {                                    // more peaks than the table holds
+            if (tid == 0) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
+            break;
+        }
+        ++n;
+        const int by = best / w, bx = best - by * w;
+        for (int i = tid; i < nc; i += blockDim.x) {
+            const int p = cand[i];
+            if (p < 0) continue;
             const int py = p / w, px = p - py * w;
-            bool dead = false;
-            for (int dy = -kRadius; dy <= kRadius && !dead; ++dy) {
-                const int qy = py + dy;
-                if (qy < 0 || qy >= h) continue;
-                for (int dx = -kRadius; dx <= kRadius; ++dx) {
-                    if (dx * dx + dy * dy > kRadius * kRadius) continue;
-                    const int qx = px + dx;
-                    if (qx < 0 || qx >= w) continue;
-                    if (state[qy * w + qx] == 2) { dead = true; break; }
-                }
-            }
-            if (dead) state[p] = 3;
+            const int dy = py - by, dx = px - bx;
+            if (dx * dx + dy * dy <= kRadius * kRadius) cand[i] = -1;   // keeps dis > dis_thres (:68); drops `best` too
         }
         __syncthreads();
     }
+    if (tid == 0) peak_counts[b * 16 + ch] = n;
 
-    // gather kept pixels, rank them by priority (kept order of the reference = descending score)
-    for (int p = tid; p < npix; p += blockDim.x)
-        if (state[p] == 2) {
-            const int i = atomicAdd(&s_n, 1);
-            if (i < LWOP_MAX_PEAKS * 4) s_list[i] = p;
-        }
-    __syncthreads();
-    const int n_all = min(s_n, LWOP_MAX_PEAKS * 4);
-    const int n = min(n_all, LWOP_MAX_PEAKS);
-    for (int i = tid; i < n_all; i += blockDim.x) {
-        const int p = s_list[i];
-        const float v = val[p];
-        int rank = 0;
-        for (int j = 0; j < n_all; ++j) {
-            const int q = s_list[j];
-            const float u = val[q];
-            rank += (u > v || (u == v && q > p)) ? 1 : 0;
-        }
-        if (rank < LWOP_MAX_PEAKS) s_sorted[rank] = p;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        peak_counts[b * 16 + ch] = n;
-        if (s_n > LWOP_MAX_PEAKS) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
-    }
-
-    // refinement (:148-183): bicubic up-sampling of the clipped 5x5 patch by `factor`,
-    // argmax (first maximum in row-major order), one warp per peak
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    // refinement (:148-183): bicubic up-sampling of the clipped 5x5 patch by `factor` (float32 two-pass,
+    // horizontal then vertical, cv2 arithmetic), argmax = first maximum in row-major order; warp per peak.
     const double scale = 1.0 / factor;              // cv2: scale_x = 1. / inv_scale_x
     for (int i = warp; i < n; i += nwarps) {
-        const int p = s_sorted[i];
+        const int p = s_kept[i];
         const int py = p / w, px = p - py * w;
         const int x0 = max(0, px - kPatchHalf), y0 = max(0, py - kPatchHalf);
         const int x1 = min(w - 1, px + kPatchHalf), y1 = min(h - 1, py + kPatchHalf);
@@ -180,25 +158,75 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
         const int dw = cv_round((double)pw * factor), dh = cv_round((double)ph * factor);
         float best_v = -INFINITY;
         int best_i = 0x7fffffff;
-        for (int d = lane; d < dw * dh; d += 32) {
-            const int oy = d / dw, ox = d - oy * dw;
-            int sx, sy;
-            float fx, fy, cx[4], cy[4];
-            src_pos(ox, scale, sx, fx);
-            src_pos(oy, scale, sy, fy);
-            cubic_coeffs(fx, cx);
-            cubic_coeffs(fy, cy);
-            float rows[4];
+        if (dw <= kRefineMax && dh <= kRefineMax) {
+            // tap tables per destination column / row
+            for (int d = lane; d < dw; d += 32) {
+                int sx;
+                float fx, c[4];
+                src_pos(d, scale, sx, fx);
+                cubic_coeffs(fx, c);
+                s_sx[warp][d] = (signed char)sx;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int yy = y0 + clampi(sy - 1 + r, 0, ph - 1);
-                float t[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) t[k] = val[yy * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
-                rows[r] = dot4(t, cx);
+                for (int k = 0; k < 4; ++k) s_cx[warp][d][k] = c[k];
             }
-            const float v = dot4(rows, cy);
-            if (v > best_v) { best_v = v; best_i = d; }
+            for (int d = lane; d < dh; d += 32) {
+                int sy;
+                float fy, c[4];
+                src_pos(d, scale, sy, fy);
+                cubic_coeffs(fy, c);
+                s_sy[warp][d] = (signed char)sy;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_cy[warp][d][k] = c[k];
+            }
+            __syncwarp();
+            // horizontal pass: every patch row at every destination column
+            for (int e = lane; e < ph * dw; e += 32) {
+                const int r = e / dw, ox = e - r * dw;
+                const int sx = s_sx[warp][ox];
+                float t[4], c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    t[k] = val[(y0 + r) * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
+                    c[k] = s_cx[warp][ox][k];
+                }
+                s_h[warp][r][ox] = dot4(t, c);
+            }
+            __syncwarp();
+            // vertical pass + running argmax
+            for (int d = lane; d < dw * dh; d += 32) {
+                const int oy = d / dw, ox = d - oy * dw;
+                const int sy = s_sy[warp][oy];
+                float t[4], c[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    t[r] = s_h[warp][clampi(sy - 1 + r, 0, ph - 1)][ox];
+                    c[r] = s_cy[warp][oy][r];
+                }
+                const float v = dot4(t, c);
+                if (v > best_v) { best_v = v; best_i = d; }
+            }
+            __syncwarp();
+        } else {
+            for (int d = lane; d < dw * dh; d += 32) {      // large factors: evaluate each destination pixel directly
+                const int oy = d / dw, ox = d - oy * dw;
+                int sx, sy;
+                float fx, fy, cx[4], cy[4];
+                src_pos(ox, scale, sx, fx);
+                src_pos(oy, scale, sy, fy);
+                cubic_coeffs(fx, cx);
+                cubic_coeffs(fy, cy);
+                float rows[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int yy = y0 + clampi(sy - 1 + r, 0, ph - 1);
+                    float t[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t[k] = val[yy * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
+                    rows[r] = dot4(t, cx);
+                }
+                const float v = dot4(rows, cy);
+                if (v > best_v) { best_v = v; best_i = d; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -359,14 +387,21 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
 // ---------------------------------------------------------------------------
 // K3: per image (one warp): joint list, greedy grouping, keypoint table.
 // ---------------------------------------------------------------------------
+constexpr int kSmemPersons = 160;   // working persons kept in shared memory; the rest spill to the global scratch
+
 __global__ void __launch_bounds__(32)
 group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_counts, const double *__restrict__ limbs,
              int *__restrict__ counts, double *__restrict__ joints, double *__restrict__ persons,
              float *__restrict__ keypoints, double *__restrict__ work) {
     const int b = blockIdx.x, lane = threadIdx.x;
     // working list of persons before the final filter: at most one new person per connection
-    double (*P)[16] = reinterpret_cast<double (*)[16]>(work + (long long)b * kMaxWorkPersons * 16);
+    __shared__ double Ps[kSmemPersons][16];
+    __shared__ float s_score[LWOP_MAX_JOINTS];           // joint scores (float32 values, exact in float)
+    __shared__ double s_conn[LWOP_MAX_PEAKS][3];         // (src_id, dst_id, score) of the current limb type
     __shared__ int s_off[LWOP_NUM_JOINTS + 1];
+    double *Pg = work + (long long)b * kMaxWorkPersons * 16;
+    auto P = [&](int k) -> double * { return k < kSmemPersons ? Ps[k] : Pg + (long long)(k - kSmemPersons) * 16; };
+
     const int *pc = peak_counts + b * 16;
     int *cnt = counts + b * LWOP_COUNTS;
     if (lane == 0) {
@@ -384,17 +419,18 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     for (int c = 0; c < LWOP_NUM_JOINTS; ++c) {                   // (x, y, score, id, 0, type) (:481-482)
         const float *pk = peaks + ((long long)b * LWOP_NUM_JOINTS + c) * LWOP_MAX_PEAKS * 4;
         for (int i = lane; i < pc[c]; i += 32) {
-            double *o = jl + (long long)(s_off[c] + i) * 6;
+            const int id = s_off[c] + i;
+            double *o = jl + (long long)id * 6;
             o[0] = pk[i * 4 + 0];
             o[1] = pk[i * 4 + 1];
             o[2] = pk[i * 4 + 2];
-            o[3] = (double)(s_off[c] + i);
+            o[3] = (double)id;
             o[4] = 0.0;
             o[5] = (double)c;
+            s_score[id] = pk[i * 4 + 2];
         }
     }
     __syncwarp();
-    __threadfence_block();
 
     int np = 0, total_conn = 0;
     bool overflow = false;
@@ -403,13 +439,19 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
         const int nconn = cnt[18 + t];
         total_conn += nconn;
         const double *rows = limbs + ((long long)b * LWOP_NUM_LIMBS + t) * LWOP_MAX_PEAKS * 5;
+        for (int e = lane; e < nconn * 3; e += 32) s_conn[e / 3][e % 3] = rows[(e / 3) * 5 + (e % 3)];
+        __syncwarp();
         for (int r = 0; r < nconn; ++r) {
-            const double a_id = rows[r * 5 + 0], b_id = rows[r * 5 + 1], s = rows[r * 5 + 2];
+            const double a_id = s_conn[r][0], b_id = s_conn[r][1], s = s_conn[r][2];
             // persons that already hold one of the two joints (:329-331)
             int nm = 0, m0 = -1, m1 = -1;
             for (int base = 0; base < np; base += 32) {
                 const int k = base + lane;
-                const bool hit = k < np && (P[k][ja] == a_id || P[k][jb] == b_id);
+                bool hit = false;
+                if (k < np) {
+                    const double *row = P(k);
+                    hit = row[ja] == a_id || row[jb] == b_id;
+                }
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int bit = __ffs(mask) - 1;
@@ -419,39 +461,46 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                     ++nm;
                 }
             }
-            const double js_b = jl[(long long)(int)b_id * 6 + 2];
+            const double js_b = (double)s_score[(int)b_id];
             if (nm == 1) {                                        // (:336-347)
-                if (lane == 0 && P[m0][jb] != b_id) {
-                    P[m0][jb] = b_id;
-                    P[m0][15] += 1.0;
-                    P[m0][14] += __dadd_rn(js_b, s);
+                double *p0 = P(m0);
+                if (lane == 0 && p0[jb] != b_id) {
+                    p0[jb] = b_id;
+                    p0[15] += 1.0;
+                    p0[14] += __dadd_rn(js_b, s);
                 }
             } else if (nm == 2) {                                 // (:348-366)
+                double *p0 = P(m0), *p1 = P(m1);
                 bool share = false;
-                if (lane < 14) share = P[m0][lane] >= 0.0 && P[m1][lane] >= 0.0;
+                if (lane < 14) share = p0[lane] >= 0.0 && p1[lane] >= 0.0;
                 share = __any_sync(0xffffffffu, share);
                 if (!share) {
-                    if (lane < 14) P[m0][lane] += __dadd_rn(P[m1][lane], 1.0);
-                    if (lane == 14) P[m0][14] = __dadd_rn(__dadd_rn(P[m0][14], P[m1][14]), s);
-                    if (lane == 15) P[m0][15] += P[m1][15];
+                    if (lane < 14) p0[lane] += __dadd_rn(p1[lane], 1.0);
+                    if (lane == 14) p0[14] = __dadd_rn(__dadd_rn(p0[14], p1[14]), s);
+                    if (lane == 15) p0[15] += p1[15];
                     __syncwarp();
+                    __threadfence_block();
                     for (int k = m1; k + 1 < np; ++k) {           // list.pop(m1)
-                        if (lane < 16) P[k][lane] = P[k + 1][lane];
+                        double v = 0.0;
+                        if (lane < 16) v = P(k + 1)[lane];
+                        if (lane < 16) P(k)[lane] = v;
                         __syncwarp();
+                        __threadfence_block();
                     }
                     --np;
                 } else if (lane == 0) {
-                    P[m0][jb] = b_id;
-                    P[m0][15] += 1.0;
-                    P[m0][14] += __dadd_rn(js_b, s);
+                    p0[jb] = b_id;
+                    p0[15] += 1.0;
+                    p0[14] += __dadd_rn(js_b, s);
                 }
             } else {                                              // 0 or >= 3 matches: new person (:367-379)
                 if (np < kMaxWorkPersons) {
-                    if (lane < 14) P[np][lane] = lane == ja ? a_id : (lane == jb ? b_id : -1.0);
-                    if (lane == 15) P[np][15] = 2.0;
+                    double *pn = P(np);
+                    if (lane < 14) pn[lane] = lane == ja ? a_id : (lane == jb ? b_id : -1.0);
+                    if (lane == 15) pn[15] = 2.0;
                     if (lane == 14) {
-                        const double js_a = jl[(long long)(int)a_id * 6 + 2];
-                        P[np][14] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, js_a), js_b), s);
+                        const double js_a = (double)s_score[(int)a_id];
+                        pn[14] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, js_a), js_b), s);
                     }
                     ++np;
                 } else {
@@ -467,25 +516,26 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     float *ko = keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
     int kept = 0;
     for (int k = 0; k < np; ++k) {
-        const bool drop = P[k][15] < 3.0 || (P[k][14] / P[k][15]) < 0.2;
+        const double *row = P(k);
+        const bool drop = row[15] < 3.0 || (row[14] / row[15]) < 0.2;
         if (drop) continue;
         if (kept >= LWOP_MAX_PERSONS) {
             overflow = true;
             break;
         }
-        if (lane < 16) po[kept * 16 + lane] = P[k][lane];
+        if (lane < 16) po[kept * 16 + lane] = row[lane];
         for (int e = lane; e < 42; e += 32) ko[kept * 42 + e] = 0.0f;
         __syncwarp();
         if (lane == 0) {
             for (int t = 0; t < LWOP_NUM_LIMBS; ++t) {
-                const double ia = P[k][c_limb_src[t]], ib = P[k][c_limb_dst[t]];
+                const double ia = row[c_limb_src[t]], ib = row[c_limb_dst[t]];
                 if (ia < 0.0 || ib < 0.0) continue;               // `-1 in joint_indices` (:411)
                 const double ids[2] = {ia, ib};
                 for (int e = 0; e < 2; ++e) {
-                    const double *row = jl + (long long)(int)ids[e] * 6;
-                    const int jt = (int)row[5];
-                    ko[kept * 42 + jt * 3 + 0] = (float)row[0];
-                    ko[kept * 42 + jt * 3 + 1] = (float)row[1];
+                    const double *jrow = jl + (long long)(int)ids[e] * 6;
+                    const int jt = (int)jrow[5];
+                    ko[kept * 42 + jt * 3 + 0] = (float)jrow[0];
+                    ko[kept * 42 + jt * 3 + 1] = (float)jrow[1];
                     ko[kept * 42 + jt * 3 + 2] = 1.0f;
                 }
             }
@@ -589,10 +639,10 @@ cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets,
 cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launches) {
     const int npix = a.h * a.w;
     if (npix > kMaxPixPerThread * 256) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)npix * 5 + 16;
-    if (smem > 96 * 1024) return cudaErrorInvalidValue;
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    const size_t smem = (size_t)npix * 8 + 16;
+    if (smem > 160 * 1024) return cudaErrorInvalidValue;
+    if (smem > 16 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int ncounts = a.B * LWOP_COUNTS;

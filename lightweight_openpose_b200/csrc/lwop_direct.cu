@@ -256,22 +256,30 @@ cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s) {
 // weights broadcast from shared memory; the output row (64 B) is written with
 // four 128-bit stores.
 // ---------------------------------------------------------------------------
+// Folded weights [27][32] (k = tap*3 + c major) and bias of the first conv live in constant
+// memory: with the 27 x 32 loop fully unrolled every FFMA takes its weight straight from
+// the constant bank (no shared-memory or register traffic for the 864 taps).
+__constant__ float c_conv1_w[27 * 32];
+__constant__ float c_conv1_b[32];
+
+cudaError_t set_conv1_constants(const float *w_host_n27 /*[32][27]*/, const float *b_host /*[32]*/) {
+    float t[27 * 32];
+    for (int n = 0; n < 32; ++n)
+        for (int k = 0; k < 27; ++k) t[k * 32 + n] = w_host_n27[n * 27 + k];
+    cudaError_t e = cudaMemcpyToSymbol(c_conv1_w, t, sizeof(t));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_conv1_b, b_host, 32 * sizeof(float));
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(128)
-conv1_bf16_kernel(const TIn *__restrict__ in, const float *__restrict__ w /*[32][9][3]*/,
-                  const float *__restrict__ bias, uint4 *__restrict__ out, int B, int H, int W, int Ho, int Wo,
+conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int Ho, int Wo,
                   int pad_t, int pad_l) {
-    __shared__ float ws[27][32];
-    __shared__ float bs[32];
     __shared__ float lut[256];   // uint8 -> float32(u8 / 255.0), the reference's `img / 255.`
-    if (sizeof(TIn) == 1)
+    if (sizeof(TIn) == 1) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)((double)i / 255.0);
-    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
-        int n = i % 32, k = i / 32;             // k = tap*3 + c
-        ws[k][n] = w[n * 27 + k];
+        __syncthreads();
     }
-    if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
-    __syncthreads();
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * Ho * Wo;
     if (p >= total) return;
@@ -281,22 +289,22 @@ conv1_bf16_kernel(const TIn *__restrict__ in, const float *__restrict__ w /*[32]
     int b = (int)(t / Ho);
     float acc[32];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = bs[n];
+    for (int n = 0; n < 32; ++n) acc[n] = c_conv1_b[n];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-        int iy = oy * 2 - pad_t + dy;
-        if (iy < 0 || iy >= H) continue;
+        const int iy = oy * 2 - pad_t + dy;
+        const bool yok = iy >= 0 && iy < H;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-            int ix = ox * 2 - pad_l + dx;
-            if (ix < 0 || ix >= W) continue;
-            const TIn *ip = in + (((long long)b * H + iy) * W + ix) * 3;
+            const int ix = ox * 2 - pad_l + dx;
+            const bool ok = yok && ix >= 0 && ix < W;
+            const TIn *ip = in + (((long long)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float v = sizeof(TIn) == 1 ? lut[(int)ip[c]] : (float)ip[c];
-                const float *wr = ws[(dy * 3 + dx) * 3 + c];
+                float v = 0.0f;
+                if (ok) v = sizeof(TIn) == 1 ? lut[(int)ip[c]] : (float)ip[c];
 #pragma unroll
-                for (int n = 0; n < 32; ++n) acc[n] = fmaf(v, wr[n], acc[n]);
+                for (int n = 0; n < 32; ++n) acc[n] = fmaf(v, c_conv1_w[((dy * 3 + dx) * 3 + c) * 32 + n], acc[n]);
             }
         }
     }
@@ -312,17 +320,16 @@ conv1_bf16_kernel(const TIn *__restrict__ in, const float *__restrict__ w /*[32]
     }
 }
 
-cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, const float *w, const float *bias, void *out, int B,
-                              int H, int W, cudaStream_t s) {
+cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s) {
     SamePad ph = same_pad(H, 3, 2, 1), pw = same_pad(W, 3, 2, 1);
     long long total = (long long)B * ph.out * pw.out;
     unsigned grid = (unsigned)((total + 127) / 128);
     if (in_is_u8)
-        conv1_bf16_kernel<uint8_t><<<grid, 128, 0, s>>>((const uint8_t *)in, w, bias, (uint4 *)out, B, H, W, ph.out,
-                                                        pw.out, ph.before, pw.before);
+        conv1_bf16_kernel<uint8_t><<<grid, 128, 0, s>>>((const uint8_t *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
+                                                        ph.before, pw.before);
     else
-        conv1_bf16_kernel<float><<<grid, 128, 0, s>>>((const float *)in, w, bias, (uint4 *)out, B, H, W, ph.out,
-                                                      pw.out, ph.before, pw.before);
+        conv1_bf16_kernel<float><<<grid, 128, 0, s>>>((const float *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
+                                                      ph.before, pw.before);
     return cudaGetLastError();
 }
 

@@ -63,11 +63,12 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
     const int sp_step = gridDim.x / p.cblocks;
     const int ch0 = cb * CB + c4 * 4;
 
-    float wt[9][4];
+    float2 wt[9][2];           // taps as fp32 pairs for the packed FFMA2
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const float4 v = *reinterpret_cast<const float4 *>(p.w + (size_t)k * p.C + ch0);
-        wt[k][0] = v.x; wt[k][1] = v.y; wt[k][2] = v.z; wt[k][3] = v.w;
+        wt[k][0] = make_float2(v.x, v.y);
+        wt[k][1] = make_float2(v.z, v.w);
     }
     if (tid == 0) {
         tma_prefetch_desc(&map_in);
@@ -101,22 +102,23 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
         const int b = t2 / p.tiles_y;
         const unsigned char *tile = smem + buf * G::kBufBytes;
 
-        float acc[G::R][4];
+        float2 acc[G::R][2];
 #pragma unroll
-        for (int r = 0; r < G::R; ++r)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[r][q] = 0.0f;
+        for (int r = 0; r < G::R; ++r) {
+            acc[r][0] = make_float2(0.0f, 0.0f);
+            acc[r][1] = make_float2(0.0f, 0.0f);
+        }
 
 #pragma unroll
         for (int ir = 0; ir < G::IRN; ++ir) {
             const int iy = rg * G::R * STRIDE + ir;
-            float v[3][4];
+            float2 v[3][2];
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = col * STRIDE + dx * DIL;
                 const uint2 raw = *reinterpret_cast<const uint2 *>(tile + ((size_t)(iy * G::IW + ix) * CB + c4 * 4) * 2);
-                v[dx][0] = bf16_lo(raw.x); v[dx][1] = bf16_hi(raw.x);
-                v[dx][2] = bf16_lo(raw.y); v[dx][3] = bf16_hi(raw.y);
+                v[dx][0] = bf16x2_to_float2(raw.x);
+                v[dx][1] = bf16x2_to_float2(raw.y);
             }
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
@@ -124,9 +126,10 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
                 if (num >= 0 && num % STRIDE == 0 && num / STRIDE < G::R) {
                     const int r = num / STRIDE;
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(v[dx][q], wt[dy * 3 + dx][q], acc[r][q]);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        acc[r][0] = ffma2(v[dx][0], wt[dy * 3 + dx][0], acc[r][0]);
+                        acc[r][1] = ffma2(v[dx][1], wt[dy * 3 + dx][1], acc[r][1]);
+                    }
                 }
             }
         }
@@ -137,8 +140,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
                 const int oy = ty * TH + rg * G::R + r;
                 if (oy < p.Ho) {
                     uint2 o;
-                    o.x = pack_bf16x2(acc[r][0], acc[r][1]);
-                    o.y = pack_bf16x2(acc[r][2], acc[r][3]);
+                    o.x = pack_bf16x2(acc[r][0].x, acc[r][0].y);
+                    o.y = pack_bf16x2(acc[r][1].x, acc[r][1].y);
                     *reinterpret_cast<uint2 *>(p.out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + ch0) = o;
                 }
             }
@@ -157,6 +160,7 @@ struct DwPlan {
     DwParams p;
     int stride, dil, cb;
     int grid;
+    int max_ctas;      // resident CTAs on the device (occupancy x SMs); the grid never exceeds it
 };
 
 namespace {
@@ -169,6 +173,17 @@ cudaError_t launch_dw_t(const DwPlan *pl, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     kfn<<<pl->grid, kDwThreads, G::kSmem, s>>>(pl->map_in, pl->p);
     return cudaGetLastError();
+}
+
+// resident CTAs per SM of the instantiation a plan will launch
+template <int STRIDE, int DIL, int CB, int TW, int TH>
+int occupancy_t() {
+    using G = DwGeom<STRIDE, DIL, CB, TW, TH>;
+    auto kfn = dw_tma_kernel<STRIDE, DIL, CB, TW, TH>;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem) != cudaSuccess) return 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, kDwThreads, G::kSmem) != cudaSuccess || n < 1) n = 1;
+    return n;
 }
 
 // tile shapes per (stride, dilation)
@@ -205,8 +220,14 @@ DwPlan *dw_plan_create(const DwArgs &a, char *err, size_t errlen) {
     p.spatial_tiles = a.B * p.tiles_x * p.tiles_y;
     int sms = gemm_num_sms();
     if (sms <= 0) sms = 148;
-    // ~3 CTAs per SM, a multiple of cblocks so each CTA keeps one channel block
-    int per_cb = (3 * sms + p.cblocks - 1) / p.cblocks;
+    int occ = 1;
+    if (a.stride == 1 && a.dil == 1) occ = cb == 64 ? occupancy_t<1, 1, 64, kTW1, kTH1>() : occupancy_t<1, 1, 32, kTW1, kTH1>();
+    else if (a.stride == 1) occ = cb == 64 ? occupancy_t<1, 2, 64, kTW1, kTH1>() : occupancy_t<1, 2, 32, kTW1, kTH1>();
+    else occ = cb == 64 ? occupancy_t<2, 1, 64, kTW2, kTH2>() : occupancy_t<2, 1, 32, kTW2, kTH2>();
+    // persistent grid = exactly the resident CTAs (one wave), a multiple of cblocks so that each CTA keeps
+    // one channel block (its taps stay in registers)
+    pl->max_ctas = occ * sms;
+    int per_cb = pl->max_ctas / p.cblocks;
     if (per_cb > p.spatial_tiles) per_cb = p.spatial_tiles;
     if (per_cb < 1) per_cb = 1;
     pl->grid = per_cb * p.cblocks;

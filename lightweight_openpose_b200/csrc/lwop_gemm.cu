@@ -57,7 +57,7 @@ struct SmemLayout {
     static constexpr int kTotal = kStagingOffset + kStagingBytes + 1024;   // + alignment slack
 };
 
-template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
@@ -79,8 +79,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int k_blocks = p.taps * p.k_blocks_per_tap;
+    // A cluster of CLUSTER CTAs works on CLUSTER consecutive M tiles of the same N tile in lock step:
+    // every CTA fetches 1/CLUSTER of the weight (B) tile and multicasts it to its peers, so the L2 -> SM
+    // traffic for B drops by CLUSTER.  m tiles past the end are dummies (zero-filled loads, clipped stores).
+    const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CLUSTER, num_clusters = gridDim.x / CLUSTER;
+    const int num_m_groups = (p.num_m_tiles + CLUSTER - 1) / CLUSTER;
+    const int num_tiles = num_m_groups * p.num_n_tiles;          // cluster-level work items
+    constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -90,7 +97,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], CLUSTER);         // one release per CTA that multicasts into this stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -102,6 +109,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int i = threadIdx.x; i < p.Cout_pad; i += kNumThreads) bias_s[i] = p.bias[i];
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();               // peers' barriers are initialised before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -110,8 +118,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
+                const int m_tile = m_group * CLUSTER + rank;
                 const long long m0 = (long long)m_tile * kBlockM;
                 int pn = 0, ph = 0, pw = 0;
                 if (IM2COL) {
@@ -135,7 +144,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     } else {
                         tma_load_2d(sa, &map_a, &full_bar[stage], c0, (int)m0);
                     }
-                    tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+                    if (CLUSTER > 1) {
+                        constexpr int kSliceRows = BLOCK_N / CLUSTER;
+                        tma_load_2d_multicast(sb + rank * kSliceRows * KSWZ, &map_b, &full_bar[stage], kb * BLOCK_K,
+                                              n_tile * BLOCK_N + rank * kSliceRows, kMask);
+                    } else {
+                        tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -147,7 +162,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -164,7 +179,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
                                      (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                    // frees the smem slot when these MMAs retire -- in every CTA that writes into it
+                    if (CLUSTER > 1) umma_commit_multicast(&empty_bar[stage], kMask);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
@@ -178,8 +195,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t acc_phase = 0;
         const bool narrow = (p.Cout != p.Cout_pad) || p.out_is_f32 || (p.out_col0 & 7) || (p.ldo & 7);
         unsigned char *stg = smem + L::kStagingOffset + q * 4096;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
+            const int m_tile = m_group * CLUSTER + rank;
             const long long m = (long long)m_tile * kBlockM + q * 32 + lane;
             const int n0 = n_tile * BLOCK_N;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -287,6 +305,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();               // nobody leaves while a peer may still write/signal here
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -357,15 +376,16 @@ struct GemmPlan {
     CUtensorMap map_a, map_b, map_out;
     GemmParams p;
     int block_n, kswz, im2col, stages;
+    int cluster;
     int grid;
     size_t smem;
 };
 
 namespace {
 
-template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
-cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
-    auto kfn = gemm_conv_kernel<BLOCK_N, KSWZ, IM2COL, STAGES>;
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER>
+cudaError_t launch_tc(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    auto kfn = gemm_conv_kernel<BLOCK_N, KSWZ, IM2COL, STAGES, CLUSTER>;
     constexpr size_t smem = SmemLayout<BLOCK_N, KSWZ, STAGES>::kTotal;
     // per-device attribute; cheap enough to set on every launch (and outside graph replay)
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -374,8 +394,25 @@ cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, flo
     if (out_override) p.out = out_override;
     if (out2_override) p.out2 = out2_override;
     if (out_override) p.use_tma_store = 0;         // the store map is bound to the plan's own output
-    kfn<<<pl->grid, kNumThreads, smem, s>>>(pl->map_a, pl->map_b, pl->map_out, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl->grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kfn, pl->map_a, pl->map_b, pl->map_out, p);
+}
+
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
+cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    if (pl->cluster == 2) return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 2>(pl, s, out_override, out2_override);
+    return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 1>(pl, s, out_override, out2_override);
 }
 
 }  // namespace
@@ -455,8 +492,13 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     p.act = d.act;
     p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
     p.num_n_tiles = d.Cout_pad / block_n;
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    pl->grid = tiles < g_num_sms ? tiles : g_num_sms;
+    // clusters of 2 CTAs share each weight tile through TMA multicast (LWOP_CLUSTER=1 disables)
+    const char *cenv = getenv("LWOP_CLUSTER");
+    pl->cluster = (cenv && atoi(cenv) == 1) ? 1 : 2;
+    if (p.num_m_tiles < 2) pl->cluster = 1;
+    const int work = ((p.num_m_tiles + pl->cluster - 1) / pl->cluster) * p.num_n_tiles;
+    const int max_clusters = g_num_sms / pl->cluster;
+    pl->grid = (work < max_clusters ? work : max_clusters) * pl->cluster;
 
     const CUtensorMapSwizzle swz = kswz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r;
@@ -496,7 +538,7 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)taps * d.Cin_pad, (cuuint64_t)d.Cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)taps * d.Cin_pad * 2};
-        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(block_n / pl->cluster)};
         cuuint32_t estr[2] = {1, 1};
         r = g_encode_tiled(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d.w_packed), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,

@@ -378,8 +378,7 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
         float *out2 = st.out2 == B_H1 ? io.h1 : st.out2 == B_P1 ? io.p1 : nullptr;
         if (st.layer == 0) {
             if (!f32) {
-                CU_OK(h, launch_conv1_bf16(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, h->blob + h->off_w[0],
-                                           h->blob + h->off_b[0], out, batch, st.H, st.W, s));
+                CU_OK(h, launch_conv1_bf16(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, batch, st.H, st.W, s));
             } else {
                 ConvArgs a{};
                 a.in = in_f32; a.in_dtype = LWOP_DT_F32; a.w = h->blob + h->off_w[0]; a.bias = h->blob + h->off_b[0];
@@ -674,6 +673,8 @@ int lwop_load_weights(lwop_handle *h, const float *host_blob, size_t num_floats)
         h->off_b[i] = off;
         off += l.cout;
     }
+    // first conv: taps in constant memory (one process drives one GPU, so the per-device symbol is unambiguous)
+    CU_OK(h, set_conv1_constants(host_blob + h->off_w[0], host_blob + h->off_b[0]));
     // bf16 operand layouts for the tensor-core path: [Cout_pad][taps][Cin_pad], bias [Cout_pad]
     for (int i = 1; i < kNumLayers; ++i) {
         const LayerSpec &l = kLayers[i];
@@ -803,9 +804,22 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
     rc = ensure_decode_scratch(h);
     if (rc != LWOP_OK) return rc;
     const size_t esz = is_u8 ? 1 : 4;
+    // LWOP_TRACE=1: timing events at the pipeline's milestones, printed to stderr (debugging aid)
+    static const bool trace = getenv("LWOP_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<std::string> tname;
+    auto mark = [&](const char *name, int k, cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+        tname.push_back(std::string(name) + std::to_string(k));
+    };
     // three streams: copy (H2D), `s` (forward), decode.  Slot k&1 holds chunk k's frames and maps; it is
     // re-used by chunk k+2 once chunk k's decode (and optional map download) has finished.
     cudaStream_t ds = h->decode_stream;
+    mark("start", 0, s);
     CU_OK(h, cudaEventRecord(h->ev_start, s));
     CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
     CU_OK(h, cudaStreamWaitEvent(ds, h->ev_start, 0));
@@ -820,11 +834,13 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
         CU_OK(h, cudaMemcpyAsync(h->slot_in[slot], (const char *)images_host + (size_t)b0 * img_elems * esz,
                                  (size_t)nb * img_elems * esz, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        mark("h2d", k, h->copy_stream);
         CU_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
         FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr};
         rc = forward_impl(h, io, nb, mode, s);
         if (rc != LWOP_OK) return rc;
         CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
+        mark("fwd", k, s);
         CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
         lwop_decode_tables t = h->own_tables;
         t.counts += (size_t)b0 * LWOP_COUNTS;
@@ -846,9 +862,22 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
             CU_OK(h, cudaMemcpyAsync(paf_host + (size_t)b0 * px * LWOP_NUM_PAFS, h->slot_paf[slot],
                                      (size_t)nb * px * LWOP_NUM_PAFS * 4, cudaMemcpyDeviceToHost, ds));
         CU_OK(h, cudaEventRecord(h->ev_done[slot], ds));
+        mark("dec", k, ds);
     }
     CU_OK(h, cudaEventRecord(h->ev_join, ds));
     CU_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (trace) {
+        rc = lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
+        mark("end", 0, s);
+        cudaStreamSynchronize(s);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            fprintf(stderr, "lwop trace: %-8s %8.3f ms\n", tname[i].c_str(), ms);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+        return rc;
+    }
     return lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
 }
 

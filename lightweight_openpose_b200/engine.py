@@ -46,27 +46,61 @@ class DecodeResult:
         self.counts = counts
 
 
-def _split_packed(batch: int, counts: np.ndarray, joints: np.ndarray, limbs: np.ndarray,
-                  persons: np.ndarray, keypoints: np.ndarray) -> List[DecodeResult]:
-    out = []
-    oj = op = oc = 0
-    for b in range(batch):
-        c = counts[b]
-        nj, npers, nconn = int(c[0]), int(c[1]), int(c[3])
-        jl = joints[oj:oj + nj].copy() if nj else np.array([])          # shape (0,) when empty (:481)
-        pa = persons[op:op + npers].copy() if npers else np.array([])   # np.array([]) (:396)
-        kp = keypoints[op:op + npers].copy().reshape(-1, 42)
+class BatchResult:
+    """Decode results of a batch, backed by the packed host arrays the C call filled.
+    ``len()``, indexing and iteration give per-image :class:`DecodeResult` objects,
+    built lazily (slicing + copying the packed rows) so that the hot path does not
+    pay for Python objects nobody looks at."""
+
+    def __init__(self, batch: int, counts: np.ndarray, joints: np.ndarray, limbs: np.ndarray,
+                 persons: np.ndarray, keypoints: np.ndarray, copy: bool = True):
+        self.batch = batch
+        c = np.array(counts[:batch], copy=True)
+        self.counts = c
+        nj, npers, nconn = int(c[:, 0].sum()), int(c[:, 1].sum()), int(c[:, 3].sum())
+        take = (lambda a, n: np.array(a[:n], copy=True)) if copy else (lambda a, n: a[:n])
+        self.joints, self.limbs = take(joints, nj), take(limbs, nconn)
+        self.persons, self.keypoints = take(persons, npers), take(keypoints, npers)
+        self._oj = np.concatenate([[0], np.cumsum(c[:, 0])])
+        self._op = np.concatenate([[0], np.cumsum(c[:, 1])])
+        self._oc = np.concatenate([[0], np.cumsum(c[:, 3])])
+
+    def __len__(self) -> int:
+        return self.batch
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(self.batch))]
+        if b < 0:
+            b += self.batch
+        if not 0 <= b < self.batch:
+            raise IndexError(b)
+        c = self.counts[b]
+        j0, j1, p0, p1 = self._oj[b], self._oj[b + 1], self._op[b], self._op[b + 1]
+        jl = self.joints[j0:j1].copy() if j1 > j0 else np.array([])          # shape (0,) when empty (:481)
+        pa = self.persons[p0:p1].copy() if p1 > p0 else np.array([])         # np.array([]) (:396)
+        kp = self.keypoints[p0:p1].copy().reshape(-1, 42)
         lim = []
-        o = oc
+        o = int(self._oc[b])
         for t in range(_lib.NUM_LIMBS):
             n = int(c[18 + t])
-            lim.append(limbs[o:o + n].copy())
+            lim.append(self.limbs[o:o + n].copy())
             o += n
-        out.append(DecodeResult(jl, pa, kp, lim, c.copy()))
-        oj += nj
-        op += npers
-        oc += nconn
-    return out
+        return DecodeResult(jl, pa, kp, lim, c.copy())
+
+    def __iter__(self):
+        return (self[b] for b in range(self.batch))
+
+    @property
+    def nbytes(self) -> int:
+        """Bytes the device->host copies of this result moved."""
+        return int(self.counts.nbytes + self.joints.nbytes + self.limbs.nbytes + self.persons.nbytes
+                   + self.keypoints.nbytes)
+
+
+def _split_packed(batch: int, counts: np.ndarray, joints: np.ndarray, limbs: np.ndarray,
+                  persons: np.ndarray, keypoints: np.ndarray) -> BatchResult:
+    return BatchResult(batch, counts, joints, limbs, persons, keypoints)
 
 
 class Engine:
@@ -220,7 +254,7 @@ class Engine:
                                         float(np.float32(thre1)), float(thre2), C.byref(s), self._stream()),
                    self.handle)
 
-    def fetch(self, batch: int) -> List[DecodeResult]:
+    def fetch(self, batch: int) -> BatchResult:
         _, s = self._device_tables()
         hst = self._host_tables(batch)
         while True:
@@ -236,7 +270,7 @@ class Engine:
                              hst["persons"].numpy(), hst["keypoints"].numpy())
 
     def decode(self, heat, paf, img_hw: Optional[Tuple[int, int]] = None, thre1: float = 0.1,
-               thre2: float = 0.0) -> List[DecodeResult]:
+               thre2: float = 0.0) -> BatchResult:
         self.decode_device(heat, paf, img_hw, thre1, thre2)
         return self.fetch(heat.shape[0])
 
