@@ -492,9 +492,11 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     p.act = d.act;
     p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
     p.num_n_tiles = d.Cout_pad / block_n;
-    // clusters of 2 CTAs share each weight tile through TMA multicast (LWOP_CLUSTER=1 disables)
+    // LWOP_CLUSTER=2: clusters of 2 CTAs share each weight tile through TMA multicast.  Measured on B200
+    // (profiles/r1_notes.md): no gain -- at cluster size 2 the multicast does not reduce L2->SM traffic,
+    // which is what bounds these kernels -- so the default stays 1.
     const char *cenv = getenv("LWOP_CLUSTER");
-    pl->cluster = (cenv && atoi(cenv) == 1) ? 1 : 2;
+    pl->cluster = (cenv && atoi(cenv) == 2) ? 2 : 1;
     if (p.num_m_tiles < 2) pl->cluster = 1;
     const int work = ((p.num_m_tiles + pl->cluster - 1) / pl->cluster) * p.num_n_tiles;
     const int max_clusters = g_num_sms / pl->cluster;
