@@ -193,6 +193,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL logs its version there)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
