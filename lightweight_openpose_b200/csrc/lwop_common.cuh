@@ -61,6 +61,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// explicit shared-space 64-bit load (keeps the compiler from emitting generic LD for smem tiles)
+__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+
 // packed fp32 FMA (Blackwell FFMA2): two independent fused multiply-adds per instruction
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);

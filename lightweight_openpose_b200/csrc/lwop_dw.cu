@@ -100,7 +100,9 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
         const int t2 = sp / p.tiles_x;
         const int ty = t2 % p.tiles_y;
         const int b = t2 / p.tiles_y;
-        const unsigned char *tile = smem + buf * G::kBufBytes;
+        // this thread's first input vector of the tile (shared-space address; everything else is an immediate offset)
+        const uint32_t tbase = smem_u32(smem + buf * G::kBufBytes) +
+                               (uint32_t)(((rg * G::R * STRIDE) * G::IW + col * STRIDE) * CB + c4 * 4) * 2u;
 
         float2 acc[G::R][2];
 #pragma unroll
@@ -111,12 +113,10 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
 
 #pragma unroll
         for (int ir = 0; ir < G::IRN; ++ir) {
-            const int iy = rg * G::R * STRIDE + ir;
             float2 v[3][2];
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const int ix = col * STRIDE + dx * DIL;
-                const uint2 raw = *reinterpret_cast<const uint2 *>(tile + ((size_t)(iy * G::IW + ix) * CB + c4 * 4) * 2);
+                const uint2 raw = lds_u64(tbase + (uint32_t)((ir * G::IW + dx * DIL) * CB * 2));
                 v[dx][0] = bf16x2_to_float2(raw.x);
                 v[dx][1] = bf16x2_to_float2(raw.y);
             }
@@ -134,16 +134,19 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
             }
         }
         const int ox = tx * TW + col;
+        const int oy0 = ty * TH + rg * G::R;
         if (ox < p.Wo) {
+            __nv_bfloat16 *op = p.out + (((size_t)b * p.Ho + oy0) * p.Wo + ox) * p.C + ch0;
+            const size_t row_pitch = (size_t)p.Wo * p.C;
 #pragma unroll
             for (int r = 0; r < G::R; ++r) {
-                const int oy = ty * TH + rg * G::R + r;
-                if (oy < p.Ho) {
+                if (oy0 + r < p.Ho) {
                     uint2 o;
                     o.x = pack_bf16x2(acc[r][0].x, acc[r][0].y);
                     o.y = pack_bf16x2(acc[r][1].x, acc[r][1].y);
-                    *reinterpret_cast<uint2 *>(p.out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.C + ch0) = o;
+                    *reinterpret_cast<uint2 *>(op) = o;
                 }
+                op += row_pitch;
             }
         }
         __syncthreads();      // every thread is done with `buf` before it is refilled next iteration

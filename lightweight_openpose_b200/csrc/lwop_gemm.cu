@@ -44,9 +44,10 @@ struct GemmParams {
     int use_tma_store;              // wide bf16 output through shared-memory staging + TMA store
 };
 
-template <int BLOCK_N, int KSWZ, int STAGES>
+template <int BLOCK_N, int KSWZ, int STAGES, int MT>
 struct SmemLayout {
-    static constexpr int kABytes = kBlockM * KSWZ;
+    static constexpr int kAHalfBytes = kBlockM * KSWZ;           // one 128-row MMA operand
+    static constexpr int kABytes = MT * kAHalfBytes;
     static constexpr int kBBytes = BLOCK_N * KSWZ;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
@@ -57,15 +58,20 @@ struct SmemLayout {
     static constexpr int kTotal = kStagingOffset + kStagingBytes + 1024;   // + alignment slack
 };
 
-template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER>
+// MT = 128-row MMA tiles per CTA tile (1 or 2): with MT = 2 one weight (B) stage feeds two MMAs, which
+// cuts the L2 -> SM traffic per flop of the N = 128 convolutions by a quarter (they are L2-bound).
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-    using L = SmemLayout<BLOCK_N, KSWZ, STAGES>;
+    using L = SmemLayout<BLOCK_N, KSWZ, STAGES, MT>;
     constexpr int BLOCK_K = KSWZ / 2;                 // bf16 elements per swizzle row
     constexpr int kMmasPerBlock = BLOCK_K / 16;
-    constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
-                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    constexpr int kTileM = kBlockM * MT;
+    constexpr int kAccCols = MT * BLOCK_N;            // TMEM columns of one accumulator stage
+    static_assert(2 * kAccCols <= 512, "accumulators do not fit in TMEM");
+    constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                   : (2 * kAccCols <= 256) ? 256 : 512;
     constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N);
 
     extern __shared__ unsigned char smem_raw[];
@@ -121,14 +127,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
                 const int m_tile = m_group * CLUSTER + rank;
-                const long long m0 = (long long)m_tile * kBlockM;
-                int pn = 0, ph = 0, pw = 0;
-                if (IM2COL) {
-                    const int hw = p.H * p.W;
-                    pn = (int)(m0 / hw);
-                    const int rem = (int)(m0 - (long long)pn * hw);
-                    ph = rem / p.W;
-                    pw = rem - ph * p.W;
+                const long long m0 = (long long)m_tile * kTileM;
+                int pn[MT], ph[MT], pw[MT];
+#pragma unroll
+                for (int hm = 0; hm < MT; ++hm) {
+                    pn[hm] = ph[hm] = pw[hm] = 0;
+                    if (IM2COL) {
+                        const long long mh = m0 + hm * kBlockM;
+                        const int hw = p.H * p.W;
+                        pn[hm] = (int)(mh / hw);
+                        const int rem = (int)(mh - (long long)pn[hm] * hw);
+                        ph[hm] = rem / p.W;
+                        pw[hm] = rem - ph[hm] * p.W;
+                    }
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -137,12 +148,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
                     const int tap = kb / p.k_blocks_per_tap;
                     const int c0 = (kb - tap * p.k_blocks_per_tap) * BLOCK_K;
-                    if (IM2COL) {
-                        const int r = tap / 3, s = tap - r * 3;
-                        tma_load_im2col_4d(sa, &map_a, &full_bar[stage], c0, pw - p.dil, ph - p.dil, pn,
-                                           (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
-                    } else {
-                        tma_load_2d(sa, &map_a, &full_bar[stage], c0, (int)m0);
+#pragma unroll
+                    for (int hm = 0; hm < MT; ++hm) {
+                        if (IM2COL) {
+                            const int r = tap / 3, s = tap - r * 3;
+                            tma_load_im2col_4d(sa + hm * L::kAHalfBytes, &map_a, &full_bar[stage], c0, pw[hm] - p.dil,
+                                               ph[hm] - p.dil, pn[hm], (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+                        } else {
+                            tma_load_2d(sa + hm * L::kAHalfBytes, &map_a, &full_bar[stage], c0,
+                                        (int)(m0 + hm * kBlockM));
+                        }
                     }
                     if (CLUSTER > 1) {
                         constexpr int kSliceRows = BLOCK_N / CLUSTER;
@@ -165,19 +180,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
-                    const uint64_t da = make_kmajor_desc<KSWZ>(sa);
                     const uint64_t db = make_kmajor_desc<KSWZ>(sb);
 #pragma unroll
-                    for (int k = 0; k < kMmasPerBlock; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
-                        umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                    for (int hm = 0; hm < MT; ++hm) {
+                        const uint64_t da = make_kmajor_desc<KSWZ>(sa + hm * L::kAHalfBytes);
+#pragma unroll
+                        for (int k = 0; k < kMmasPerBlock; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+                            umma_bf16_ss(d_tmem + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                         kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     // frees the smem slot when these MMAs retire -- in every CTA that writes into it
                     if (CLUSTER > 1) umma_commit_multicast(&empty_bar[stage], kMask);
@@ -198,11 +216,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
             const int m_tile = m_group * CLUSTER + rank;
-            const long long m = (long long)m_tile * kBlockM + q * 32 + lane;
             const int n0 = n_tile * BLOCK_N;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+          for (int hm = 0; hm < MT; ++hm) {
+            const long long m = (long long)m_tile * kTileM + hm * kBlockM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + hm * BLOCK_N);
             const bool row_ok = m < p.M;
             if (BLOCK_N >= 64 && p.use_tma_store) {
                 // ---- wide bf16 output: 64 columns at a time -> swizzled staging -> one TMA store per warp ----
@@ -212,7 +232,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64), r0);
                     tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + 32), r1);
                     tmem_ld_wait();
-                    if (g == BLOCK_N / 64 - 1) {             // accumulator drained: hand it back to the MMA warp
+                    if (g == BLOCK_N / 64 - 1 && hm == MT - 1) {   // accumulator drained: hand it back to the MMA warp
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -246,11 +266,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&map_out, stg, p.out_col0 + n0 + g * 64, m_tile * kBlockM + q * 32);
+                        tma_store_2d(&map_out, stg, p.out_col0 + n0 + g * 64, m_tile * kTileM + hm * kBlockM + q * 32);
                         bulk_commit_group();
                     }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
 #pragma unroll 1
@@ -296,9 +315,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }   // hm
+            if (!(BLOCK_N >= 64 && p.use_tma_store)) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) bulk_wait_all();                      // outstanding TMA stores complete before exit
@@ -377,16 +399,17 @@ struct GemmPlan {
     GemmParams p;
     int block_n, kswz, im2col, stages;
     int cluster;
+    int mt;
     int grid;
     size_t smem;
 };
 
 namespace {
 
-template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER>
+template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES, int CLUSTER, int MT>
 cudaError_t launch_tc(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
-    auto kfn = gemm_conv_kernel<BLOCK_N, KSWZ, IM2COL, STAGES, CLUSTER>;
-    constexpr size_t smem = SmemLayout<BLOCK_N, KSWZ, STAGES>::kTotal;
+    auto kfn = gemm_conv_kernel<BLOCK_N, KSWZ, IM2COL, STAGES, CLUSTER, MT>;
+    constexpr size_t smem = SmemLayout<BLOCK_N, KSWZ, STAGES, MT>::kTotal;
     // per-device attribute; cheap enough to set on every launch (and outside graph replay)
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -411,13 +434,18 @@ cudaError_t launch_tc(const GemmPlan *pl, cudaStream_t s, void *out_override, fl
 
 template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
 cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
-    if (pl->cluster == 2) return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 2>(pl, s, out_override, out2_override);
-    return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 1>(pl, s, out_override, out2_override);
+    if (pl->cluster == 2) return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 2, 1>(pl, s, out_override, out2_override);
+    return launch_tc<BLOCK_N, KSWZ, IM2COL, STAGES, 1, 1>(pl, s, out_override, out2_override);
 }
 
 }  // namespace
 
 cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    if (pl->mt == 2) {      // 256-row CTA tiles, N = 128, 4 stages of 48 KB
+        if (pl->block_n != 128 || pl->kswz != 128) return cudaErrorInvalidValue;
+        return pl->im2col ? launch_tc<128, 128, true, 4, 1, 2>(pl, s, out_override, out2_override)
+                          : launch_tc<128, 128, false, 4, 1, 2>(pl, s, out_override, out2_override);
+    }
     if (pl->im2col) {
         if (pl->block_n == 128 && pl->kswz == 128) return launch_t<128, 128, true, 6>(pl, s, out_override, out2_override);
         return cudaErrorInvalidValue;
@@ -490,13 +518,17 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     p.ldr = d.ldr;
     p.out_is_f32 = d.out_dtype == LWOP_DT_F32;
     p.act = d.act;
-    p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+    // 256-row tiles for the N = 128 convolutions with a deep K (3x3: K = 1152); LWOP_MT=1 disables
+    const char *mtenv = getenv("LWOP_MT");
+    pl->mt = (block_n == 128 && kswz == 128 && taps * d.Cin_pad >= 512 && M >= 4096 && !(mtenv && atoi(mtenv) == 1)) ? 2 : 1;
+    const int tile_m = kBlockM * pl->mt;
+    p.num_m_tiles = (int)((M + tile_m - 1) / tile_m);
     p.num_n_tiles = d.Cout_pad / block_n;
     // LWOP_CLUSTER=2: clusters of 2 CTAs share each weight tile through TMA multicast.  Measured on B200
     // (profiles/r1_notes.md): no gain -- at cluster size 2 the multicast does not reduce L2->SM traffic,
     // which is what bounds these kernels -- so the default stays 1.
     const char *cenv = getenv("LWOP_CLUSTER");
-    pl->cluster = (cenv && atoi(cenv) == 2) ? 2 : 1;
+    pl->cluster = (cenv && atoi(cenv) == 2 && pl->mt == 1) ? 2 : 1;
     if (p.num_m_tiles < 2) pl->cluster = 1;
     const int work = ((p.num_m_tiles + pl->cluster - 1) / pl->cluster) * p.num_n_tiles;
     const int max_clusters = g_num_sms / pl->cluster;
