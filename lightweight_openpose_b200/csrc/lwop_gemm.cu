@@ -26,7 +26,7 @@ namespace lwop {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;        // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kEpilogueWarp0 = 4;
 
 struct GemmParams {
@@ -54,8 +54,10 @@ struct SmemLayout {
     static constexpr int kBiasOffset = kBarOffset + 256;
     // epilogue staging for TMA stores: 4 warps x (32 rows x 128 B), 1024-byte aligned (128B swizzle)
     static constexpr int kStagingOffset = ((kBiasOffset + 512 * 4 + 1023) / 1024) * 1024;
-    static constexpr int kStagingBytes = BLOCK_N >= 64 ? 4 * 4096 : 0;
-    static constexpr int kTotal = kStagingOffset + kStagingBytes + 1024;   // + alignment slack
+    static constexpr int kStagingBytes = BLOCK_N >= 64 ? 8 * 4096 : 0;   // one 4 KB tile per epilogue warp
+    // dynamic shared memory of a kernel without static __shared__ starts at the CTA's window base
+    // (1024-byte aligned); the kernel traps if that ever fails to hold
+    static constexpr int kTotal = kStagingOffset + kStagingBytes;
 };
 
 // MT = 128-row MMA tiles per CTA tile (1 or 2): with MT = 2 one weight (B) stage feeds two MMAs, which
@@ -74,9 +76,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                    : (2 * kAccCols <= 256) ? 256 : 512;
     constexpr uint32_t kIdesc = make_idesc_bf16(kBlockM, BLOCK_N);
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                                            ~static_cast<uintptr_t>(1023));
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full = empty_bar + STAGES;
@@ -208,12 +213,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp >= kEpilogueWarp0) {
         // ===================== epilogue =====================
-        const int q = warp - kEpilogueWarp0;                 // TMEM lane quarter == warp % 4
-        int acc = 0;
+        // Two epilogue groups of 4 warps; group g owns accumulator stage g and therefore every other tile
+        // of this CTA, so the drain of tile i overlaps the drain of tile i+1 as well as its MMAs.
+        const int q = (warp - kEpilogueWarp0) & 3;           // TMEM lane quarter == warp % 4
+        const int grp = (warp - kEpilogueWarp0) >> 2;
+        const int acc = grp;
         uint32_t acc_phase = 0;
         const bool narrow = (p.Cout != p.Cout_pad) || p.out_is_f32 || (p.out_col0 & 7) || (p.ldo & 7);
-        unsigned char *stg = smem + L::kStagingOffset + q * 4096;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        unsigned char *stg = smem + L::kStagingOffset + (grp * 4 + q) * 4096;
+        int local_tile = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local_tile) {
+            if ((local_tile & 1) != grp) continue;
             const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
             const int m_tile = m_group * CLUSTER + rank;
             const int n0 = n_tile * BLOCK_N;
@@ -239,18 +249,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     if (lane == 0) bulk_wait_read_all();     // previous store has finished reading the staging tile
                     __syncwarp();
-                    const float *bs = bias_s + n0 + g * 64;
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0 + g * 64);
                     const uint4 *rp = (p.residual && row_ok)
                                           ? reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + n0 + g * 64)
                                           : nullptr;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {            // 8 columns = one 16-byte chunk
                         float v[8];
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int c = j * 8 + e;
                             const uint32_t raw = c < 32 ? r0[c] : r1[c - 32];
-                            v[e] = apply_act_fast(__uint_as_float(raw) + bs[c], p.act);
+                            v[e] = apply_act_fast(__uint_as_float(raw) + bb[e], p.act);
                         }
                         if (rp) {
                             const uint4 rr = rp[j];
@@ -321,7 +333,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;                                  // this group's stage is used once per two tiles
         }
         if (lane == 0) bulk_wait_all();                      // outstanding TMA stores complete before exit
     }
@@ -441,10 +453,15 @@ cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, flo
 }  // namespace
 
 cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
-    if (pl->mt == 2) {      // 256-row CTA tiles, N = 128, 4 stages of 48 KB
-        if (pl->block_n != 128 || pl->kswz != 128) return cudaErrorInvalidValue;
-        return pl->im2col ? launch_tc<128, 128, true, 4, 1, 2>(pl, s, out_override, out2_override)
-                          : launch_tc<128, 128, false, 4, 1, 2>(pl, s, out_override, out2_override);
+    if (pl->mt == 2) {      // 256-row CTA tiles
+        if (pl->block_n == 128 && pl->kswz == 128)          // 4 stages of 48 KB
+            return pl->im2col ? launch_tc<128, 128, true, 4, 1, 2>(pl, s, out_override, out2_override)
+                              : launch_tc<128, 128, false, 4, 1, 2>(pl, s, out_override, out2_override);
+        if (pl->block_n == 64 && pl->kswz == 128 && !pl->im2col)
+            return launch_tc<64, 128, false, 4, 1, 2>(pl, s, out_override, out2_override);
+        if (pl->block_n == 64 && pl->kswz == 64 && !pl->im2col)
+            return launch_tc<64, 64, false, 8, 1, 2>(pl, s, out_override, out2_override);
+        return cudaErrorInvalidValue;
     }
     if (pl->im2col) {
         if (pl->block_n == 128 && pl->kswz == 128) return launch_t<128, 128, true, 6>(pl, s, out_override, out2_override);
@@ -463,6 +480,8 @@ cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_overr
     }
     return cudaErrorInvalidValue;
 }
+
+static inline bool im2col_early(int ksize) { return ksize == 3; }
 
 GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     if (!gemm_driver_ready(err, errlen)) return nullptr;
@@ -520,7 +539,10 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     p.act = d.act;
     // 256-row tiles for the N = 128 convolutions with a deep K (3x3: K = 1152); LWOP_MT=1 disables
     const char *mtenv = getenv("LWOP_MT");
-    pl->mt = (block_n == 128 && kswz == 128 && taps * d.Cin_pad >= 512 && M >= 4096 && !(mtenv && atoi(mtenv) == 1)) ? 2 : 1;
+    const int mt_mode = mtenv ? atoi(mtenv) : 0;     // 0 = heuristic, 1 = never, 2 = wherever the tile shapes allow
+    const bool mt_legal = M >= 4096 && ((block_n == 128 && kswz == 128) || (block_n == 64 && !im2col_early(d.ksize)));
+    const bool mt_heur = block_n == 128 && kswz == 128 && taps * d.Cin_pad >= 512;
+    pl->mt = (mt_legal && mt_mode != 1 && (mt_heur || mt_mode == 2)) ? 2 : 1;
     const int tile_m = kBlockM * pl->mt;
     p.num_m_tiles = (int)((M + tile_m - 1) / tile_m);
     p.num_n_tiles = d.Cout_pad / block_n;

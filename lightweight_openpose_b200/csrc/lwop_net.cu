@@ -823,9 +823,11 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
     CU_OK(h, cudaEventRecord(h->ev_start, s));
     CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
     CU_OK(h, cudaStreamWaitEvent(ds, h->ev_start, 0));
+    // chunk schedule: a half-size first chunk shortens the only upload that nothing can hide
     int k = 0;
-    for (int b0 = 0; b0 < batch; b0 += chunk, ++k) {
-        const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    for (int b0 = 0, nb = 0; b0 < batch; b0 += nb, ++k) {
+        nb = (k == 0 && batch > chunk && chunk >= 16) ? chunk / 2 : chunk;
+        if (nb > batch - b0) nb = batch - b0;
         const int slot = k & 1;
         if (k >= 2) {
             CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_fwd[slot], 0));   // frames of chunk k-2 consumed
