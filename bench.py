@@ -168,6 +168,10 @@ def run_reference(args, rank: int, world: int):
 # ---------------------------------------------------------------------------
 def classify_step(desc):
     layer, is_dw, h, w, cin, cout, k, stride, dil, tc = desc
+    if tc == 2:
+        return "sep_fused_dw3x3_pw1x1"
+    if tc == 3:
+        return None              # pointwise half of a fused separable layer: no launch of its own
     if is_dw:
         return "depthwise3x3"
     if layer == 0:
@@ -198,7 +202,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     batch = args.batch
-    eng = engine.Engine(H, W, max_batch=batch, device=local_rank)
+    eng = engine.Engine(H, W, max_batch=batch, device=local_rank, fuse_separable=not args.no_fuse)
     variables, source = checkpoint.load_or_synthesize()
     eng.load_variables(variables, source)
 
@@ -300,9 +304,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             acc += np.asarray(eng.profile_forward(x_dev, mode=args.mode))
         acc /= n_prof
         classes = {}
-        for d, ms in zip(descs, acc):
-            c = classes.setdefault(classify_step(d), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        for i, (d, ms) in enumerate(zip(descs, acc)):
+            cls = classify_step(d)
+            if cls is None:
+                continue
+            c = classes.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             fl, by = step_work(d, batch)
+            if d[9] == 2:        # fused: depthwise + pointwise flops; bytes = layer input + layer output only
+                fl2, _ = step_work(descs[i + 1], batch)
+                oh, ow = -(-d[2] // d[7]), -(-d[3] // d[7])
+                fl += fl2
+                by = 2.0 * (d[2] * d[3] * d[4] + oh * ow * descs[i + 1][5]) * batch
             c["ms"] += ms
             c["flops"] += fl
             c["bytes"] += by
@@ -310,7 +322,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         peaks = measured_peaks()
         dom = max(classes, key=lambda k: classes[k]["ms"])
         dc = classes[dom]
-        if dom.startswith("gemm"):
+        # a fused separable layer is bounded by whichever of the two rooflines is slower for its shape mix:
+        # report it against the tensor roofline when its tensor time exceeds its HBM time
+        tensor_bound = dom.startswith("gemm") or (dom.startswith("sep") and
+                                                  dc["flops"] / (peaks["bf16_tflops_sustained"] * 1e12) >
+                                                  dc["bytes"] / (peaks["hbm_gbs"] * 1e9))
+        if tensor_bound:
             achieved = dc["flops"] / (dc["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
@@ -321,7 +338,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         roof["kernel"] = dom
         roof["launches_per_step"] = dc["launches"]
         roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
-        roof["peak_source"] = peaks["source"] + (" (sustained)" if dom.startswith("gemm") else "")
+        roof["peak_source"] = peaks["source"] + (" (sustained)" if tensor_bound else "")
         per_class = {}
         for k, c in classes.items():
             per_class[k] = {"ms": round(c["ms"], 4), "launches": c["launches"],
@@ -330,10 +347,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         fwd_ms = float(acc.sum())
         if args.dump_steps:
             with open(args.dump_steps, "w") as fh:
-                for d, ms in zip(descs, acc):
+                for i, (d, ms) in enumerate(zip(descs, acc)):
+                    if classify_step(d) is None:
+                        continue
                     fl, by = step_work(d, batch)
+                    if d[9] == 2:
+                        fl += step_work(descs[i + 1], batch)[0]
+                        by = 2.0 * (d[2] * d[3] * d[4] + d[2] * d[3] * descs[i + 1][5]) * batch
                     fh.write(json.dumps({"layer": d[0], "kind": classify_step(d), "in_hw": [d[2], d[3]], "cin": d[4],
-                                         "cout": d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
+                                         "cout": descs[i + 1][5] if d[9] == 2 else d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
                                          "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
                                          "gbs": round(by / (ms * 1e-3) / 1e9, 1)}) + "\n")
 
@@ -391,6 +413,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
     ap.add_argument("--cpu-images", type=int, default=16, help="frames in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="separable layers as two kernels (A/B timing of the fusion)")
     ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage of the host-buffer path (0 = library default)")
     ap.add_argument("--sweep-chunks", action="store_true", help="also time the host-buffer path for several chunk sizes")
     ap.add_argument("--dump-steps", default=None, help="write per-kernel timings (one JSON object per line) here")

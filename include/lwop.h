@@ -57,7 +57,8 @@ extern "C" {
 #define LWOP_DT_BF16  1
 
 /* lwop_create flags */
-#define LWOP_FLAG_NO_GRAPH   1u    /* launch kernels directly instead of replaying a CUDA graph */
+#define LWOP_FLAG_NO_GRAPH      1u /* launch kernels directly instead of replaying a CUDA graph */
+#define LWOP_FLAG_NO_FUSE_SEP   2u /* separable layers as two kernels (depthwise, then 1x1 GEMM) instead of the fused one */
 
 /* network constants (reference src/train_config.py:25-26,31) */
 #define LWOP_NUM_JOINTS   14
@@ -178,6 +179,17 @@ int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype,
                       int batch, int height, int width, int channels,
                       const float *w_dev, int stride, int dilation, void *out_dev, void *stream);
 
+/* conv_dw() / conv_dw_no_bn(): tf.layers.separable_conv2d (depthwise 3x3 then pointwise 1x1, nothing in
+ * between) + folded batch norm / bias + activation (net_factory.py:15-19,25-29), optional residual added after
+ * the activation (lightweight_openpose.py:27).  LWOP_MODE_BF16: ONE fused kernel (CUDA-core depthwise feeding
+ * the tcgen05 GEMM through shared memory); needs bf16 tensors, stride 1, dilation 1 or 2 and
+ * (cin, cout) in {(32, 64), (64k, 128), (64k, 256m)}, else LWOP_ERR_UNSUPPORTED.
+ * dw_w_dev float32 [9][cin], pw_w_dev float32 [cout][cin], bias_dev float32 [cout] or NULL;
+ * in_dev / residual_dev / out_dev bf16 NHWC. */
+int lwop_separable_conv2d(lwop_handle *h, int mode, const void *in_dev, int batch, int height, int width, int cin,
+                          const float *dw_w_dev, const float *pw_w_dev, const float *bias_dev, int cout,
+                          int dilation, int act, const void *residual_dev, void *out_dev, void *stream);
+
 /* output size of a 'same' conv: ceil(in / stride) */
 int lwop_same_out(int in, int stride);
 
@@ -185,7 +197,9 @@ int lwop_same_out(int in, int stride);
 uint32_t lwop_crc32c(const void *data, size_t nbytes);
 
 /* Layer program introspection and per-kernel timing (bench.py's live roofline).
- * lwop_step_desc fills out[10] = {layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, uses_tcgen05}.
+ * lwop_step_desc fills out[10] = {layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, kernel} with
+ * kernel 0 = CUDA-core kernel, 1 = tcgen05 GEMM, 2 = fused depthwise+pointwise tcgen05 kernel (this depthwise step
+ * and the pointwise step after it), 3 = no launch (the pointwise half absorbed into the previous step).
  * lwop_profile_forward runs one forward WITHOUT the CUDA graph, bracketing every
  * kernel with CUDA events on `stream`, synchronises and writes the per-step
  * durations in milliseconds to step_ms[lwop_num_steps()]. */

@@ -77,6 +77,20 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
 }
+// packed fp32 add (Blackwell FADD2)
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+// ReLU + round-to-nearest-even pack of two fp32 values into bf16x2 (lo in the low half): one instruction
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }

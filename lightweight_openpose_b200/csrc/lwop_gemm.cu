@@ -406,6 +406,20 @@ bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuin
     return true;
 }
 
+bool encode_tiled_f32(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,
+                      const cuuint64_t *strides_bytes, const cuuint32_t *box, char *err, size_t errlen) {
+    if (!gemm_driver_ready(err, errlen)) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                                strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled (fp32, rank %d) failed: CUresult %d", rank, (int)r);
+        return false;
+    }
+    return true;
+}
+
 struct GemmPlan {
     CUtensorMap map_a, map_b, map_out;
     GemmParams p;

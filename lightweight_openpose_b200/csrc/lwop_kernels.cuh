@@ -67,12 +67,32 @@ bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuin
                        const cuuint64_t *strides_bytes, const cuuint32_t *box, int swizzle_bytes, char *err,
                        size_t errlen);
 
+bool encode_tiled_f32(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,
+                      const cuuint64_t *strides_bytes, const cuuint32_t *box, char *err, size_t errlen);
+
 // lwop_dw.cu -- TMA-staged depthwise 3x3
 struct DwPlan;
 bool dw_plan_supported(int C, int stride, int dil);
 DwPlan *dw_plan_create(const DwArgs &a, char *err, size_t errlen);
 void dw_plan_destroy(DwPlan *p);
 cudaError_t dw_plan_launch(const DwPlan *p, cudaStream_t s);
+
+// lwop_sep.cu -- fused depthwise 3x3 -> pointwise 1x1 (tcgen05), stride 1
+struct SepPlan;
+struct SepConvDesc {
+    const void *in;            // bf16 NHWC [B,H,W,C]
+    const float *dw_w;         // fp32 [9][C] (device)
+    const void *w_packed;      // bf16 [Cout_pad][C] pointwise weights (BN folded)
+    const float *bias;         // fp32 [Cout_pad]
+    const void *residual;      // bf16 NHWC [B,H,W,ldr] or nullptr (added after the activation)
+    void *out;                 // bf16 NHWC [B,H,W,ldo], written at column offset out_col0
+    int B, H, W, C, Cout_pad, dil, act;
+    int ldo, out_col0, ldr;
+};
+bool sep_plan_supported(int C, int Cout_pad, int stride, int dil);
+SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen);
+void sep_plan_destroy(SepPlan *p);
+cudaError_t sep_plan_launch(const SepPlan *p, cudaStream_t s);
 
 // lwop_decode.cu
 struct DecodeArgs {

@@ -87,6 +87,8 @@ int pad_cin(int c) { return c == 40 ? 64 : c; }
 struct PlanSet {
     std::vector<GemmPlan *> plans;   // per step (nullptr for non-GEMM steps)
     std::vector<DwPlan *> dw;        // per step (nullptr for non-depthwise steps)
+    std::vector<SepPlan *> sep;      // per step: fused depthwise -> pointwise plan, stored at the depthwise step
+    int launches = 0;                // kernels one forward launches with these plans
 };
 
 struct GraphEntry {
@@ -94,6 +96,7 @@ struct GraphEntry {
     const void *in = nullptr;
     void *heat = nullptr, *paf = nullptr, *h1 = nullptr, *p1 = nullptr;
     int in_u8 = 0;
+    int launches = 0;
 };
 
 }  // namespace
@@ -255,6 +258,8 @@ void destroy_plans(lwop_handle *h) {
             if (p) gemm_plan_destroy(p);
         for (DwPlan *p : kv.second.dw)
             if (p) dw_plan_destroy(p);
+        for (SepPlan *p : kv.second.sep)
+            if (p) sep_plan_destroy(p);
     }
     h->plan_sets.clear();
     for (auto &kv : h->graphs)
@@ -272,6 +277,18 @@ void destroy_graphs_only(lwop_handle *h) {
 
 bool step_uses_gemm(const Step &s) { return !s.is_dw && s.layer != 0; }
 
+// A depthwise step and the pointwise step that follows it run as ONE fused kernel (lwop_sep.cu) when the
+// shape is supported; LWOP_FLAG_NO_FUSE_SEP / LWOP_NO_FUSE_SEP=1 keep the two-kernel path (A/B timing).
+bool step_fuses_with_next(const lwop_handle *h, size_t i) {
+    static const bool env_off = getenv("LWOP_NO_FUSE_SEP") != nullptr;
+    if (env_off || (h->flags & LWOP_FLAG_NO_FUSE_SEP)) return false;
+    if (i + 1 >= h->steps.size()) return false;
+    const Step &s = h->steps[i], &n = h->steps[i + 1];
+    if (!s.is_dw || n.is_dw || n.layer != s.layer || n.out_f32 || n.out2 >= 0) return false;
+    const LayerSpec &l = kLayers[s.layer];
+    return sep_plan_supported(l.cin, pad_cout(l.cout), l.stride, l.dil);
+}
+
 int get_plans(lwop_handle *h, int batch, PlanSet **out) {
     auto it = h->plan_sets.find(batch);
     if (it != h->plan_sets.end()) {
@@ -281,16 +298,38 @@ int get_plans(lwop_handle *h, int batch, PlanSet **out) {
     PlanSet ps;
     ps.plans.assign(h->steps.size(), nullptr);
     ps.dw.assign(h->steps.size(), nullptr);
+    ps.sep.assign(h->steps.size(), nullptr);
     char err[256];
     auto cleanup = [&]() {
         for (GemmPlan *p : ps.plans)
             if (p) gemm_plan_destroy(p);
         for (DwPlan *p : ps.dw)
             if (p) dw_plan_destroy(p);
+        for (SepPlan *p : ps.sep)
+            if (p) sep_plan_destroy(p);
     };
     for (size_t i = 0; i < h->steps.size(); ++i) {
         const Step &s = h->steps[i];
         const LayerSpec &l = kLayers[s.layer];
+        if (step_fuses_with_next(h, i)) {
+            const Step &n = h->steps[i + 1];
+            SepConvDesc d{};
+            d.in = h->arena_bf16[s.in];
+            d.dw_w = h->blob + h->off_dw[s.layer];
+            d.w_packed = h->w_bf16[s.layer];
+            d.bias = h->b_pad[s.layer];
+            d.residual = n.res >= 0 ? h->arena_bf16[n.res] : nullptr;
+            d.out = h->arena_bf16[n.out];
+            d.B = batch; d.H = s.H; d.W = s.W; d.C = l.cin; d.Cout_pad = pad_cout(l.cout); d.dil = l.dil; d.act = l.act;
+            d.ldo = n.ldo; d.out_col0 = n.col0; d.ldr = 128;
+            ps.sep[i] = sep_plan_create(d, err, sizeof(err));
+            if (!ps.sep[i]) {
+                cleanup();
+                return fail(h, LWOP_ERR_UNSUPPORTED, std::string("layer ") + std::to_string(s.layer) + " (fused separable): " + err);
+            }
+            ++i;           // the pointwise step is part of the fused kernel
+            continue;
+        }
         if (s.is_dw) {
             DwArgs a{};
             a.in = h->arena_bf16[s.in]; a.out = h->arena_bf16[s.out]; a.dtype = LWOP_DT_BF16;
@@ -390,6 +429,12 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
             h->launches++;
             continue;
         }
+        if (mode == LWOP_MODE_BF16 && ps->sep[i]) {
+            CU_OK(h, sep_plan_launch(ps->sep[i], s));
+            h->launches++;
+            continue;
+        }
+        if (mode == LWOP_MODE_BF16 && i > 0 && ps->sep[i - 1]) continue;   // pointwise half of the fused kernel above
         if (st.is_dw) {
             DwArgs a{};
             a.in = in; a.out = out; a.dtype = dt; a.w = h->blob + h->off_dw[st.layer];
@@ -454,8 +499,10 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
         }
         // One eager pass first: creates the plans (tensor-map encoding calls the driver), sets the
         // per-kernel shared-memory attributes and surfaces launch errors outside of stream capture.
+        const long long eager_before = h->launches;
         rc = run_forward(h, batch, mode, io, s);
         if (rc != LWOP_OK) return rc;
+        const int launches_per_forward = (int)(h->launches - eager_before);
         CU_OK(h, cudaStreamSynchronize(s));
         cudaStream_t cs;
         CU_OK(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -479,12 +526,13 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
         cudaStreamDestroy(cs);
         if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
         ne.in = io.in; ne.heat = io.heat; ne.paf = io.paf; ne.h1 = io.h1; ne.p1 = io.p1; ne.in_u8 = io.in_u8;
+        ne.launches = launches_per_forward;
         cache.push_back(ne);
         gp = &cache.back();
     }
     GraphEntry &g = *gp;
     CU_OK(h, cudaGraphLaunch(g.exec, s));
-    h->launches += (long long)h->steps.size();
+    h->launches += g.launches;
     return LWOP_OK;
 }
 
@@ -973,6 +1021,46 @@ int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype, i
     return LWOP_OK;
 }
 
+int lwop_separable_conv2d(lwop_handle *h, int mode, const void *in_dev, int batch, int height, int width, int cin,
+                          const float *dw_w_dev, const float *pw_w_dev, const float *bias_dev, int cout,
+                          int dilation, int act, const void *residual_dev, void *out_dev, void *stream) {
+    if (!h || !in_dev || !dw_w_dev || !pw_w_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (mode != LWOP_MODE_BF16) return fail(h, LWOP_ERR_UNSUPPORTED, "fused separable conv exists in bf16 mode only");
+    const int cout_pad = pad_cout(cout);
+    if (cout != cout_pad || !sep_plan_supported(cin, cout_pad, 1, dilation))
+        return fail(h, LWOP_ERR_UNSUPPORTED, "fused separable conv: unsupported (cin, cout, dilation)");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    void *wp = nullptr;
+    float *bp = nullptr;
+    CU_OK(h, cudaMalloc(&wp, (size_t)cout_pad * cin * 2));
+    CU_OK(h, cudaMalloc(&bp, (size_t)cout_pad * 4));
+    CU_OK(h, cudaMemsetAsync(bp, 0, (size_t)cout_pad * 4, s));
+    CU_OK(h, launch_pack_bf16(pw_w_dev, wp, (long long)cout, cin, cin, s));
+    if (bias_dev) CU_OK(h, cudaMemcpyAsync(bp, bias_dev, (size_t)cout * 4, cudaMemcpyDeviceToDevice, s));
+    SepConvDesc d{};
+    d.in = in_dev; d.dw_w = dw_w_dev; d.w_packed = wp; d.bias = bp; d.residual = residual_dev; d.out = out_dev;
+    d.B = batch; d.H = height; d.W = width; d.C = cin; d.Cout_pad = cout_pad; d.dil = dilation; d.act = act;
+    d.ldo = cout; d.out_col0 = 0; d.ldr = cout;
+    char err[256];
+    SepPlan *pl = sep_plan_create(d, err, sizeof(err));
+    int rc = LWOP_OK;
+    if (!pl) {
+        rc = fail(h, LWOP_ERR_UNSUPPORTED, err);
+    } else {
+        cudaError_t e = sep_plan_launch(pl, s);
+        h->launches += 2;
+        if (e != cudaSuccess) rc = fail(h, LWOP_ERR_CUDA, std::string("fused separable launch: ") + cudaGetErrorString(e));
+        cudaError_t e2 = cudaStreamSynchronize(s);
+        if (rc == LWOP_OK && e2 != cudaSuccess)
+            rc = fail(h, LWOP_ERR_CUDA, std::string("fused separable kernel: ") + cudaGetErrorString(e2));
+        sep_plan_destroy(pl);
+    }
+    cudaFree(wp);
+    cudaFree(bp);
+    return rc;
+}
+
 uint32_t lwop_crc32c(const void *data, size_t n) {
     std::call_once(g_crc_once, crc_init);
     const unsigned char *p = (const unsigned char *)data;
@@ -1008,6 +1096,8 @@ int lwop_step_desc(const lwop_handle *h, int step, int *out10) {
     out10[7] = (st.is_dw || st.layer == 0) ? l.stride : 1;
     out10[8] = (st.is_dw || l.kind == L_CONV) ? l.dil : 1;
     out10[9] = step_uses_gemm(st) ? 1 : 0;
+    if (step_fuses_with_next(h, (size_t)step)) out10[9] = 2;                      // fused dw -> pw kernel runs here
+    else if (step > 0 && step_fuses_with_next(h, (size_t)step - 1)) out10[9] = 3; // absorbed into the previous step
     return LWOP_OK;
 }
 

@@ -1,0 +1,673 @@
+// Fused separable convolution: depthwise 3x3 (stride 1, dilation 1/2) -> pointwise 1x1 on the
+// tensor cores, one kernel, the depthwise result never leaves the SM.
+//
+//   out[pixel, n] = act( sum_c dw(x)[pixel, c] * Wpw[n, c] + bias[n] ) (+ residual)
+//   dw(x)[pixel, c] = sum_{3x3 taps} x[pixel + tap*dil, c] * Wdw[tap, c]          ('same' zero padding)
+//
+// This is tf.layers.separable_conv2d as the reference uses it (src/net_factory.py:15-19 conv_dw with
+// the folded batch norm + ReLU, :25-29 conv_dw_no_bn with ELU; nothing sits between the depthwise and
+// the pointwise half) plus the tf.add of lightweight_openpose.py:27 as an optional residual.
+//
+// CTA tile = an 8 x 16 patch of output pixels (= the 128 rows of one tcgen05 MMA) x BLOCK_N output
+// channels; K (= input channels) is walked in chunks of CB channels:
+//   warp 3      TMA producer: per chunk ONE 4D box load of the input patch + halo (zero OOB fill is the
+//               'same' padding) plus the chunk's 9 x CB depthwise taps into a slab ring
+//   warp 0      TMA producer: the [BLOCK_N x CB] pointwise weight tiles into the B ring
+//   warps 4-11  depthwise producers (CUDA cores): slab -> 9-tap fp32 FMA (packed FFMA2) -> bf16 ->
+//               written straight into the A ring in the 128B/64B-swizzled K-major layout the MMA
+//               expects (generic-proxy stores, released through the mbarrier; the MMA thread crosses to
+//               the async proxy with one fence.proxy.async per chunk after its acquire)
+//   warp 1      tcgen05.mma issuer (A from the dw warps, B from TMA), fp32 accumulators in TMEM
+//   warp 2      TMEM allocator
+//   warps 12-19 epilogue, two groups of 4 warps: tcgen05.ld -> bias / activation / residual -> bf16 ->
+//               swizzled staging -> 4D TMA store (the patch is clipped at the image border by the store)
+// Two accumulator schemes (template NH):
+//   NH = 1  BLOCK_N <= 256 columns per tile, two accumulator stages; epilogue group g owns stage g (every
+//           other tile), so the drain of tile i overlaps the main loop of tile i+1.  Cout = 512 would need
+//           two N tiles per pixel patch, i.e. the depthwise work done twice.
+//   NH = 2  Cout = 512: ONE pass over the patch feeds two N = 256 MMAs per K chunk (all 512 TMEM columns,
+//           one accumulator stage); group h drains half h.  The depthwise producers are the slower side of
+//           this pipeline (~73.7k fp32 FMAs per chunk vs 1024 tensor cycles), and they run ahead through
+//           the A ring while the epilogue drains, so the single accumulator stage costs little.
+// Compared with the depthwise kernel followed by the 1x1 GEMM this removes one HBM write and one HBM
+// read of the [B,H,W,C] intermediate per layer.
+#include <stdlib.h>
+
+#include "lwop_kernels.cuh"
+
+namespace lwop {
+
+namespace {
+
+constexpr int kTW = 16, kTH = 8;                 // output patch (w x h) = 128 GEMM rows
+constexpr int kDwWarp0 = 4, kDwWarps = 8, kDwThreads = kDwWarps * 32;
+constexpr int kEpiWarp0 = 12, kEpiWarps = 8;               // two epilogue groups of 4 warps (one per TMEM lane quarter)
+constexpr int kSepThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 640
+
+struct SepParams {
+    const float *dw_w;              // [9][C] fp32
+    const float *bias;              // [Cout_pad]
+    const __nv_bfloat16 *residual;  // NHWC [B,H,W,ldr] or nullptr
+    int B, H, W, C;
+    int Cout_pad;
+    int tiles_x, tiles_y, num_m_tiles, num_n_tiles;
+    int k_blocks;                   // C / CB
+    int act, ldr, out_col0;
+    unsigned long long *prof;       // optional [16] stall counters (LWOP_SEP_PROF=1), nullptr otherwise
+};
+
+// stall accounting (debugging aid): cycles one elected thread of each role spends in each barrier wait
+enum { PF_TOTAL = 0, PF_TMA_SLAB_EMPTY, PF_TMA_AB_EMPTY, PF_MMA_TMEM_EMPTY, PF_MMA_B_FULL, PF_MMA_A_FULL,
+       PF_DW_SLAB_FULL, PF_DW_AB_EMPTY, PF_DW_COMPUTE, PF_EPI_TMEM_FULL, PF_EPI_STORE_WAIT, PF_EPI_WORK, PF_N };
+
+#define PF_WAIT(slot, stmt)                                     \
+    do {                                                        \
+        if (pf) {                                               \
+            const long long _t0 = clock64();                    \
+            stmt;                                               \
+            pf_acc[slot] += (unsigned long long)(clock64() - _t0); \
+        } else {                                                \
+            stmt;                                               \
+        }                                                       \
+    } while (0)
+
+template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS>
+struct SepSmem {
+    static constexpr int KSWZ = 2 * CB;                      // bytes per K-major operand row
+    static constexpr int kABytes = 128 * KSWZ;
+    static constexpr int kBBytes = BLOCK_N * KSWZ;
+    static constexpr int IW = kTW + 2 * DIL, IH = kTH + 2 * DIL;
+    static constexpr int kSlabPix = IW * IH * CB * 2;        // input patch + halo, bf16
+    static constexpr int kTapBytes = 9 * CB * 4;             // this chunk's depthwise taps, fp32 [9][CB]
+    static constexpr int kSlabTx = kSlabPix + kTapBytes;
+    static constexpr int kSlabBytes = ((kSlabTx + 127) / 128) * 128;
+    static constexpr int kAOff = 0;
+    static constexpr int kBOff = kAOff + SA * kABytes;
+    static constexpr int kStagingOff = kBOff + SB * kBBytes; // 8 epilogue warps x 2 KB (32 rows x 32 bf16, 64B swizzle)
+    static constexpr int kSlabOff = kStagingOff + kEpiWarps * 2048;
+    static constexpr int kBarOff = kSlabOff + SS * kSlabBytes;
+    static constexpr int kNumBars = 2 * SS + 2 * SA + 2 * SB + 4;
+    static constexpr int kBiasOff = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
+    static constexpr int kTotal = kBiasOff + 512 * 4;
+    static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand stages must stay 1 KB aligned");
+    static_assert(kSlabPix % 128 == 0, "tap block must stay 128-byte aligned for TMA");
+    static_assert(kTotal <= 232448, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ void tma_store_4d(const void *desc, const void *smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+// bf16 pair -> fp32 pair on the ALU pipe (PRMT), leaving the FMA pipe to the packed FMAs
+__device__ __forceinline__ float2 unpack_bf16x2_prmt(uint32_t v) {
+    uint32_t lo, hi;
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(v));
+    asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(hi) : "r"(v));
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS, int NH, bool PROF>
+__global__ void __launch_bounds__(kSepThreads, 1)
+sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_taps,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                const SepParams p) {
+    using L = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS>;
+    constexpr int KSWZ = L::KSWZ;
+    constexpr int kMmasPerBlock = CB / 16;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(2 * BLOCK_N <= 512, "two accumulator stages / halves must fit in TMEM");
+    static_assert(NH == 1 || NH == 2, "NH");
+    constexpr uint32_t kIdesc = make_idesc_bf16(128, BLOCK_N);
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    uint64_t *slab_full = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
+    uint64_t *slab_empty = slab_full + SS;
+    uint64_t *a_full = slab_empty + SS;
+    uint64_t *a_empty = a_full + SA;
+    uint64_t *b_full = a_empty + SA;
+    uint64_t *b_empty = b_full + SB;
+    uint64_t *tmem_full = b_empty + SB;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOff);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    constexpr bool pf = PROF;
+    unsigned long long pf_acc[PROF ? PF_N : 1];
+#pragma unroll
+    for (int i = 0; i < (PROF ? PF_N : 1); ++i) pf_acc[i] = 0;
+    const long long pf_start = PROF ? clock64() : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_in);
+        tma_prefetch_desc(&map_taps);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SS; ++i) {
+            mbar_init(&slab_full[i], 1);
+            mbar_init(&slab_empty[i], kDwWarps);
+        }
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&a_full[i], kDwWarps);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);             // one arrival per warp of the epilogue group
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+    for (int i = threadIdx.x; i < p.Cout_pad; i += kSepThreads) bias_s[i] = p.bias[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer: pointwise weight tiles (B ring) =====================
+        if (lane == 0) {
+            int sb = 0;
+            uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        PF_WAIT(PF_TMA_AB_EMPTY, mbar_wait(&b_empty[sb], bph ^ 1));
+                        mbar_arrive_expect_tx(&b_full[sb], L::kBBytes);
+                        tma_load_2d(smem + L::kBOff + sb * L::kBBytes, &map_b, &b_full[sb], kb * CB,
+                                    (n_tile * NH + h) * BLOCK_N);
+                        if (++sb == SB) { sb = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA producer: input slabs + depthwise taps (own thread, so that a full B ring
+        // never delays the loads the depthwise warps are waiting for) =====================
+        if (lane == 0) {
+            int ss = 0;
+            uint32_t sph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int b = m_tile / tiles_per_img;
+                const int t2 = m_tile - b * tiles_per_img;
+                const int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    PF_WAIT(PF_TMA_SLAB_EMPTY, mbar_wait(&slab_empty[ss], sph ^ 1));
+                    unsigned char *slab = smem + L::kSlabOff + ss * L::kSlabBytes;
+                    mbar_arrive_expect_tx(&slab_full[ss], L::kSlabTx);
+                    tma_load_4d(slab, &map_in, &slab_full[ss], kb * CB, tx * kTW - DIL, ty * kTH - DIL, b);
+                    tma_load_2d(slab + L::kSlabPix, &map_taps, &slab_full[ss], kb * CB, 0);
+                    if (++ss == SS) { ss = 0; sph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t aph = 0, bph = 0;
+            int local_tile = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+                // NH = 1: accumulator stage = local_tile & 1 (used every other tile); NH = 2: half h, used every tile
+                const int acc = NH == 1 ? (local_tile & 1) : 0;
+                const uint32_t acc_phase = NH == 1 ? (uint32_t)((local_tile >> 1) & 1) : (uint32_t)(local_tile & 1);
+                if (NH == 1) {
+                    PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
+                    tcgen05_fence_after();
+                }
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    PF_WAIT(PF_MMA_A_FULL, mbar_wait(&a_full[sa], aph));
+                    // the A stage was written with ordinary (generic-proxy) stores released through a_full;
+                    // this fence makes them visible to the tensor core's async-proxy reads issued below
+                    fence_proxy_async();
+                    const uint64_t da = make_kmajor_desc<KSWZ>(smem_u32(smem + L::kAOff + sa * L::kABytes));
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        if (NH == 2 && kb == 0) PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait(&tmem_empty[h], acc_phase ^ 1));
+                        PF_WAIT(PF_MMA_B_FULL, mbar_wait(&b_full[sb], bph));
+                        tcgen05_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((NH == 1 ? acc : h) * BLOCK_N);
+                        const uint64_t db = make_kmajor_desc<KSWZ>(smem_u32(smem + L::kBOff + sb * L::kBBytes));
+#pragma unroll
+                        for (int k = 0; k < kMmasPerBlock; ++k)
+                            umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&b_empty[sb]);
+                        if (++sb == SB) { sb = 0; bph ^= 1; }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == SA) { sa = 0; aph ^= 1; }
+                }
+                if (NH == 1) {
+                    umma_commit(&tmem_full[acc]);
+                } else {
+                    umma_commit(&tmem_full[0]);
+                    umma_commit(&tmem_full[1]);
+                }
+            }
+        }
+    } else if (warp >= kDwWarp0 && warp < kDwWarp0 + kDwWarps) {
+        // ===================== depthwise producers =====================
+        int sa = 0, ss = 0;
+        uint32_t aph = 0, sph = 0;
+        if constexpr (CB == 64) {
+            // One warp = one 4 x 4 block of output pixels x all 64 channels of the chunk; lane = channel pair.
+            // Every LDS.32 / STS.32 of a warp touches one full 128-byte pixel row (one shared-memory wavefront),
+            // and a (4+2d)^2 input block feeds 16 outputs: 2.25 (d=1) loads per output instead of 9.
+            constexpr int IB = 4 + 2 * DIL;                     // input block edge
+            const int wq = warp - kDwWarp0;
+            const int bx = wq & 3, by = wq >> 2;
+            const uint32_t slab_off = (uint32_t)((((by * 4) * L::IW + bx * 4) * CB + lane * 2) * 2);
+            const uint32_t tap_off = (uint32_t)(L::kSlabPix + lane * 8);
+            // A row m = (by*4 + oy)*16 + bx*4 + ox; 128B swizzle phase m & 7 = ((bx & 1)*4 + ox)
+            uint32_t a_col[4];
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox)
+                a_col[ox] = (uint32_t)(((by * 4) * kTW + bx * 4 + ox) * 128 +
+                                       ((((lane >> 2) ^ (((bx & 1) << 2) | ox)) << 4) | ((lane & 3) << 2)));
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    float2 acc[4][4];
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+                        for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = make_float2(0.0f, 0.0f);
+                    PF_WAIT(PF_DW_SLAB_FULL, mbar_wait(&slab_full[ss], sph));
+                    const long long pf_c0 = pf ? clock64() : 0;
+                    const uint32_t sbase = smem_u32(smem + L::kSlabOff + ss * L::kSlabBytes);
+                    const uint32_t tbase = sbase + slab_off;
+                    float2 wt[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const uint2 v = lds_u64(sbase + tap_off + (uint32_t)(k * CB * 4));
+                        wt[k] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+                    }
+#pragma unroll
+                    for (int iy = 0; iy < IB; ++iy) {
+                        float2 v[IB];
+#pragma unroll
+                        for (int ix = 0; ix < IB; ++ix) {
+                            uint32_t raw;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw)
+                                         : "r"(tbase + (uint32_t)((iy * L::IW + ix) * CB * 2)));
+                            v[ix] = unpack_bf16x2_prmt(raw);
+                        }
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const int oy = iy - dy * DIL;
+                            if (oy >= 0 && oy < 4) {
+#pragma unroll
+                                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                                    for (int dx = 0; dx < 3; ++dx)
+                                        acc[oy][ox] = ffma2(v[ox + dx * DIL], wt[dy * 3 + dx], acc[oy][ox]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
+                    if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
+                    PF_WAIT(PF_DW_AB_EMPTY, mbar_wait(&a_empty[sa], aph ^ 1));   // the MMAs that read this A stage retired
+                    const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes);
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+                        for (int ox = 0; ox < 4; ++ox)
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(abase + a_col[ox] + (uint32_t)(oy * kTW * 128)),
+                                         "r"(pack_bf16x2(acc[oy][ox].x, acc[oy][ox].y))
+                                         : "memory");
+                    __syncwarp();                                          // orders the lanes' stores before lane 0's release
+                    if (lane == 0) mbar_arrive(&a_full[sa]);
+                    if (++ss == SS) { ss = 0; sph ^= 1; }
+                    if (++sa == SA) { sa = 0; aph ^= 1; }
+                }
+            }
+        } else {
+        constexpr int TPP = CB / 4;                    // threads per pixel (4 channels each)
+        constexpr int SLOTS = kDwThreads / TPP;        // pixel columns in flight
+        constexpr int ROWG = SLOTS / kTW;              // row groups
+        constexpr int R = kTH / ROWG;                  // output rows per thread
+        constexpr int IRN = R + 2 * DIL;               // input rows one thread walks
+        static_assert(SLOTS % kTW == 0 && ROWG >= 1 && kTH % ROWG == 0, "bad depthwise mapping");
+        const int t = threadIdx.x - kDwWarp0 * 32;
+        const int c4 = t % TPP, slot = t / TPP;
+        const int col = slot % kTW, rg = slot / kTW;
+        // this thread's 8 bytes inside a swizzled operand row: 16-byte chunk (c4 >> 1) XOR the row's swizzle phase;
+        // row m = (rg*R + r)*16 + col, so the phase depends on col only (128B: m & 7, 64B: (m >> 1) & 3)
+        const int swz = KSWZ == 128 ? (col & 7) : ((col >> 1) & 3);
+        const uint32_t a_off = (uint32_t)(((rg * R) * kTW + col) * KSWZ + ((((c4 >> 1) ^ swz) << 4) | ((c4 & 1) << 3)));
+        const uint32_t slab_off = (uint32_t)((((rg * R) * L::IW + col) * CB + c4 * 4) * 2);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                float2 acc[R][2];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r][0] = make_float2(0.0f, 0.0f);
+                    acc[r][1] = make_float2(0.0f, 0.0f);
+                }
+                PF_WAIT(PF_DW_SLAB_FULL, mbar_wait(&slab_full[ss], sph));
+                const long long pf_c0 = pf ? clock64() : 0;
+                const uint32_t sbase = smem_u32(smem + L::kSlabOff + ss * L::kSlabBytes);
+                const uint32_t tbase = sbase + slab_off;
+                float2 wt[9][2];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint4 v = lds_u128(sbase + (uint32_t)(L::kSlabPix + (k * CB + c4 * 4) * 4));
+                    wt[k][0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+                    wt[k][1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+                }
+#pragma unroll
+                for (int ir = 0; ir < IRN; ++ir) {
+                    float2 v[3][2];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const uint2 raw = lds_u64(tbase + (uint32_t)((ir * L::IW + dx * DIL) * CB * 2));
+                        v[dx][0] = unpack_bf16x2_prmt(raw.x);
+                        v[dx][1] = unpack_bf16x2_prmt(raw.y);
+                    }
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int r = ir - dy * DIL;
+                        if (r >= 0 && r < R) {
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                acc[r][0] = ffma2(v[dx][0], wt[dy * 3 + dx][0], acc[r][0]);
+                                acc[r][1] = ffma2(v[dx][1], wt[dy * 3 + dx][1], acc[r][1]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
+                if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
+                PF_WAIT(PF_DW_AB_EMPTY, mbar_wait(&a_empty[sa], aph ^ 1));   // the MMAs that read this A stage retired
+                const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes) + a_off;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t lo = pack_bf16x2(acc[r][0].x, acc[r][0].y), hi = pack_bf16x2(acc[r][1].x, acc[r][1].y);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(abase + (uint32_t)(r * kTW * KSWZ)), "r"(lo),
+                                 "r"(hi)
+                                 : "memory");
+                }
+                __syncwarp();                                          // orders the lanes' stores before lane 0's release
+                if (lane == 0) mbar_arrive(&a_full[sa]);
+                if (++ss == SS) { ss = 0; sph ^= 1; }
+                if (++sa == SA) { sa = 0; aph ^= 1; }
+            }
+        }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue =====================
+        const int q = (warp - kEpiWarp0) & 3;                 // TMEM lane quarter == warp % 4
+        const int grp = (warp - kEpiWarp0) >> 2;              // NH = 1: accumulator stage; NH = 2: column half
+        unsigned char *stg = smem + L::kStagingOff + (grp * 4 + q) * 2048;
+        int local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            if (NH == 1 && (local_tile & 1) != grp) continue;
+            const uint32_t acc_phase = NH == 1 ? (uint32_t)((local_tile >> 1) & 1) : (uint32_t)(local_tile & 1);
+            const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+            const int b = m_tile / tiles_per_img;
+            const int t2 = m_tile - b * tiles_per_img;
+            const int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+            const int n0 = (NH == 1 ? n_tile : n_tile * NH + grp) * BLOCK_N;
+            const int py = ty * kTH + q * 2 + (lane >> 4), px = tx * kTW + (lane & 15);
+            const bool row_ok = py < p.H && px < p.W;
+            const size_t pix = ((size_t)b * p.H + py) * p.W + px;
+            PF_WAIT(PF_EPI_TMEM_FULL, mbar_wait(&tmem_full[grp], acc_phase));
+            const long long pf_e0 = pf ? clock64() : 0;
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BLOCK_N);
+#pragma unroll 1
+            for (int g = 0; g < BLOCK_N / 32; ++g) {
+                uint32_t r0[32];
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 32), r0);
+                tmem_ld_wait();
+                if (g == BLOCK_N / 32 - 1) {                  // accumulator drained: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[grp]);
+                }
+                if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());   // previous store has finished reading the staging tile
+                __syncwarp();
+                const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0 + g * 32);
+                const uint4 *rp = (p.residual && row_ok)
+                                      ? reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + n0 + g * 32)
+                                      : nullptr;
+                if (p.act == LWOP_ACT_RELU && !p.residual) {
+                    // conv_dw layers (folded BN + ReLU): packed bias add, then ReLU + bf16 pack in one instruction
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(r0[j * 8 + 0]), __uint_as_float(r0[j * 8 + 1])),
+                                                make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(r0[j * 8 + 2]), __uint_as_float(r0[j * 8 + 3])),
+                                                make_float2(b0.z, b0.w));
+                        const float2 s2 = fadd2(make_float2(__uint_as_float(r0[j * 8 + 4]), __uint_as_float(r0[j * 8 + 5])),
+                                                make_float2(b1.x, b1.y));
+                        const float2 s3 = fadd2(make_float2(__uint_as_float(r0[j * 8 + 6]), __uint_as_float(r0[j * 8 + 7])),
+                                                make_float2(b1.z, b1.w));
+                        uint4 o;
+                        o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
+                        o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
+                        *reinterpret_cast<uint4 *>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+                    }
+                } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                 // 8 columns = one 16-byte chunk
+                    float v[8];
+                    const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = apply_act_fast(__uint_as_float(r0[j * 8 + e]) + bb[e], p.act);
+                    if (rp) {
+                        const uint4 rr = rp[j];
+                        v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                        v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                    }
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    // 64B swizzle: 16-byte chunk index XOR ((row >> 1) & 3)
+                    *reinterpret_cast<uint4 *>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+                }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    // box = (32 channels, 16 columns, 2 rows, 1 image): rows of the staging tile in the same order
+                    tma_store_4d(&map_out, stg, p.out_col0 + n0 + g * 32, tx * kTW, ty * kTH + q * 2, b);
+                    bulk_commit_group();
+                }
+            }
+            if (pf) pf_acc[PF_EPI_WORK] += (unsigned long long)(clock64() - pf_e0);
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    if (pf && lane == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == kDwWarp0 || warp == kEpiWarp0)) {
+        if (warp == 0) pf_acc[PF_TOTAL] = (unsigned long long)(clock64() - pf_start);
+#pragma unroll
+        for (int i = 0; i < (PROF ? PF_N : 1); ++i)
+            if (pf_acc[i]) atomicAdd(p.prof + i, pf_acc[i]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace
+
+struct SepPlan {
+    CUtensorMap map_in, map_taps, map_b, map_out;
+    SepParams p;
+    int block_n, cb, dil, nh;
+    int grid;
+};
+
+namespace {
+
+template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS, int NH>
+cudaError_t launch_sep_t(const SepPlan *pl, cudaStream_t s) {
+    constexpr int smem = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS>::kTotal;
+    if (pl->p.prof) {
+        auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, true>;
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<pl->grid, kSepThreads, smem, s>>>(pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+        return cudaGetLastError();
+    }
+    auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, false>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kfn<<<pl->grid, kSepThreads, smem, s>>>(pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool sep_plan_supported(int C, int Cout_pad, int stride, int dil) {
+    if (stride != 1 || (dil != 1 && dil != 2)) return false;
+    if (!(C == 32 || C % 64 == 0)) return false;
+    if (C == 32) return Cout_pad == 64 && dil == 1;
+    if (Cout_pad % 256 == 0) return true;
+    return Cout_pad == 128 && dil == 1;
+}
+
+SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
+    if (!gemm_driver_ready(err, errlen)) return nullptr;
+    if (!sep_plan_supported(d.C, d.Cout_pad, 1, d.dil)) {
+        snprintf(err, errlen, "fused separable conv: unsupported C=%d Cout_pad=%d dil=%d", d.C, d.Cout_pad, d.dil);
+        return nullptr;
+    }
+    if (!d.out || (d.ldo % 8) != 0 || (d.out_col0 % 8) != 0) {
+        snprintf(err, errlen, "fused separable conv: output pitch / column offset must be multiples of 8");
+        return nullptr;
+    }
+    SepPlan *pl = (SepPlan *)calloc(1, sizeof(SepPlan));
+    pl->cb = d.C == 32 ? 32 : 64;
+    pl->block_n = d.Cout_pad % 256 == 0 ? 256 : d.Cout_pad;
+    pl->dil = d.dil;
+    SepParams &p = pl->p;
+    p.dw_w = d.dw_w;
+    p.bias = d.bias;
+    p.residual = (const __nv_bfloat16 *)d.residual;
+    p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C;
+    p.Cout_pad = d.Cout_pad;
+    p.tiles_x = (d.W + kTW - 1) / kTW;
+    p.tiles_y = (d.H + kTH - 1) / kTH;
+    p.num_m_tiles = d.B * p.tiles_x * p.tiles_y;
+    // Cout = 512: both N = 256 halves in one pass over the patch (LWOP_SEP_NH1=1 keeps two N tiles, for A/B timing)
+    pl->nh = (d.Cout_pad == 512 && !getenv("LWOP_SEP_NH1")) ? 2 : 1;
+    p.num_n_tiles = d.Cout_pad / (pl->block_n * pl->nh);
+    p.k_blocks = d.C / pl->cb;
+    p.act = d.act;
+    p.ldr = d.ldr;
+    p.out_col0 = d.out_col0;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int sms = gemm_num_sms();
+    if (sms <= 0) sms = 148;
+    pl->grid = tiles < sms ? tiles : sms;
+    {   // input patch + halo: box (CB channels, 16 + 2d columns, 8 + 2d rows, 1 image), zero OOB fill
+        cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.C * 2, (cuuint64_t)d.W * d.C * 2, (cuuint64_t)d.H * d.W * d.C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)pl->cb, (cuuint32_t)(kTW + 2 * d.dil), (cuuint32_t)(kTH + 2 * d.dil), 1};
+        if (!encode_tiled_bf16(&pl->map_in, 4, d.in, dims, strides, box, 0, err, errlen)) {
+            free(pl);
+            return nullptr;
+        }
+    }
+    {   // depthwise taps [9][C] fp32: the chunk's (CB, 9) block rides along with the slab
+        cuuint64_t dims[2] = {(cuuint64_t)d.C, 9};
+        cuuint64_t strides[1] = {(cuuint64_t)d.C * 4};
+        cuuint32_t box[2] = {(cuuint32_t)pl->cb, 9};
+        if (!encode_tiled_f32(&pl->map_taps, 2, d.dw_w, dims, strides, box, err, errlen)) {
+            free(pl);
+            return nullptr;
+        }
+    }
+    {   // pointwise weights [Cout_pad][C] bf16, K-major tiles of (CB, BLOCK_N)
+        cuuint64_t dims[2] = {(cuuint64_t)d.C, (cuuint64_t)d.Cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)d.C * 2};
+        cuuint32_t box[2] = {(cuuint32_t)pl->cb, (cuuint32_t)pl->block_n};
+        if (!encode_tiled_bf16(&pl->map_b, 2, d.w_packed, dims, strides, box, 2 * pl->cb, err, errlen)) {
+            free(pl);
+            return nullptr;
+        }
+    }
+    {   // output NHWC [B,H,W,ldo]: per epilogue warp a (32 channels, 16 columns, 2 rows) box, clipped at the border
+        cuuint64_t dims[4] = {(cuuint64_t)d.ldo, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 2, (cuuint64_t)d.W * d.ldo * 2, (cuuint64_t)d.H * d.W * d.ldo * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)kTW, 2, 1};
+        if (!encode_tiled_bf16(&pl->map_out, 4, d.out, dims, strides, box, 64, err, errlen)) {
+            free(pl);
+            return nullptr;
+        }
+    }
+    return pl;
+}
+
+void sep_plan_destroy(SepPlan *p) { free(p); }
+
+static cudaError_t sep_plan_launch_inner(const SepPlan *pl, cudaStream_t s);
+
+cudaError_t sep_plan_launch(const SepPlan *pl, cudaStream_t s) {
+    static const bool prof = getenv("LWOP_SEP_PROF") != nullptr;
+    if (!prof) return sep_plan_launch_inner(pl, s);
+    // debugging aid: per-role stall cycles, averaged per CTA, printed to stderr (synchronises)
+    static const char *names[PF_N] = {"total", "tma:slab_empty", "tma:ab_empty", "mma:tmem_empty", "mma:b_full",
+                                      "mma:a_full", "dw:slab_full", "dw:ab_empty", "dw:compute", "epi:tmem_full",
+                                      "epi:store_wait", "epi:work"};
+    unsigned long long *d = nullptr, hbuf[PF_N];
+    cudaMalloc(&d, PF_N * sizeof(unsigned long long));
+    cudaMemsetAsync(d, 0, PF_N * sizeof(unsigned long long), s);
+    SepPlan tmp = *pl;
+    tmp.p.prof = d;
+    cudaError_t e = sep_plan_launch_inner(&tmp, s);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    fprintf(stderr, "lwop sep prof: C=%d N=%d dil=%d HxW=%dx%d B=%d grid=%d |", pl->p.C, pl->p.Cout_pad, pl->dil, pl->p.H,
+            pl->p.W, pl->p.B, pl->grid);
+    for (int i = 0; i < PF_N; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hbuf[i] / pl->grid);
+    fprintf(stderr, "\n");
+    return e;
+}
+
+static cudaError_t sep_plan_launch_inner(const SepPlan *pl, cudaStream_t s) {
+    if (pl->cb == 32) return launch_sep_t<64, 32, 1, 2, 3, 6, 1>(pl, s);
+    if (pl->block_n == 128) return launch_sep_t<128, 64, 1, 2, 4, 4, 1>(pl, s);
+    if (pl->nh == 2) {
+        if (pl->dil == 2) return launch_sep_t<256, 64, 2, 2, 3, 2, 2>(pl, s);
+        return launch_sep_t<256, 64, 1, 2, 3, 3, 2>(pl, s);
+    }
+    if (pl->dil == 2) return launch_sep_t<256, 64, 2, 2, 3, 2, 1>(pl, s);
+    return launch_sep_t<256, 64, 1, 2, 3, 3, 1>(pl, s);
+}
+
+}  // namespace lwop

@@ -106,14 +106,15 @@ def _split_packed(batch: int, counts: np.ndarray, joints: np.ndarray, limbs: np.
 class Engine:
     """One per (device, H, W).  Not thread-safe: serialise calls per engine."""
 
-    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, use_graph: bool = True):
+    def __init__(self, height: int, width: int, max_batch: int = 1, device: int = 0, use_graph: bool = True,
+                 fuse_separable: bool = True):
         require_gpu(device)
         self.lib = _lib.load()
         self.device = device
         self.height, self.width, self.max_batch = height, width, max_batch
         self.map_h, self.map_w = graph.output_hw(height, width)
         h = C.c_void_p()
-        flags = 0 if use_graph else _lib.FLAG_NO_GRAPH
+        flags = (0 if use_graph else _lib.FLAG_NO_GRAPH) | (0 if fuse_separable else _lib.FLAG_NO_FUSE_SEP)
         _lib.check(self.lib.lwop_create(device, max_batch, height, width, flags, C.byref(h)))
         self.handle = h
         self.weights_source: Optional[str] = None
@@ -309,7 +310,8 @@ class Engine:
         return res
 
     def step_descs(self):
-        """[(layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, uses_tcgen05), ...]"""
+        """[(layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, kernel), ...] with kernel
+        0 = CUDA cores, 1 = tcgen05 GEMM, 2 = fused depthwise+pointwise (runs at this step), 3 = absorbed."""
         n = self.lib.lwop_num_steps(self.handle)
         out = []
         buf = (C.c_int * 10)()

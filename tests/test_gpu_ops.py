@@ -146,3 +146,49 @@ def test_depthwise_kernels(eng, case, kind):
     want = ref_conv_nhwc(x, w, None, 3, stride, dil, 0, depthwise=True)
     tol = 2.0 ** -8 * max(1.0, float(np.abs(want).max())) if vec else 1e-5
     assert np.abs(out.float().cpu().numpy() - want).max() <= tol
+
+
+SEP_CASES = [
+    # B, H, W, cin, cout, dil, act, residual
+    (2, 184, 184, 32, 64, 1, 1, False),      # backbone layer 1: K = 32 (64B swizzle), one K chunk per tile
+    (2, 92, 92, 128, 128, 1, 1, False),      # layer 3
+    (2, 46, 46, 256, 256, 1, 1, False),      # layer 5
+    (2, 46, 46, 256, 512, 1, 1, False),      # layer 6: two N tiles
+    (3, 46, 46, 512, 512, 2, 1, False),      # layer 7: dilation 2
+    (2, 46, 46, 512, 512, 1, 1, False),      # layers 8-11
+    (2, 46, 46, 128, 128, 1, 2, True),       # Cpm: ELU + tf.add
+    (1, 23, 37, 128, 128, 1, 2, False),      # odd, non-square, patches clipped at the border
+    (1, 7, 5, 64, 256, 2, 1, False),         # map smaller than one patch
+    (5, 16, 32, 128, 256, 1, 0, False),      # exact patches, linear
+]
+
+
+@pytest.mark.parametrize("case", SEP_CASES)
+def test_fused_separable_kernel(eng, case):
+    """conv_dw / conv_dw_no_bn as ONE kernel (depthwise on CUDA cores feeding the tcgen05 GEMM):
+    reference = float64 depthwise, rounded to bf16 (the operand the tensor core sees), float64 pointwise."""
+    B, H, W, cin, cout, dil, act, use_res = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    x = bf16_round(rng.normal(size=(B, H, W, cin)))
+    dw = (rng.normal(size=(9, cin)) / 3.0).astype(np.float32)
+    pw = bf16_round(rng.normal(size=(cout, 1, cin)) / np.sqrt(cin))
+    b = rng.normal(size=(cout,)).astype(np.float32)
+    res = bf16_round(rng.normal(size=(B, H, W, cout))) if use_res else None
+    xd = torch.from_numpy(x).cuda().to(torch.bfloat16)
+    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device="cuda")
+    dwd, pwd, bd = torch.from_numpy(dw).cuda(), torch.from_numpy(pw).cuda(), torch.from_numpy(b).cuda()
+    resd = torch.from_numpy(res).cuda().to(torch.bfloat16) if use_res else None
+    rc = eng.lib.lwop_separable_conv2d(eng.handle, _lib.MODE_BF16, xd.data_ptr(), B, H, W, cin, dwd.data_ptr(),
+                                       pwd.data_ptr(), bd.data_ptr(), cout, dil, act,
+                                       resd.data_ptr() if use_res else None, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, eng.handle)
+    torch.cuda.synchronize()
+    mid = ref_conv_nhwc(x, dw, None, 3, 1, dil, 0, depthwise=True)
+    mid_lo = bf16_round(mid)
+    want = ref_conv_nhwc(mid_lo, pw, b, 1, 1, 1, act, res)
+    # the kernel's fp32 depthwise may round a mid value to the neighbouring bf16: allow a few such flips per row
+    slack = ref_conv_nhwc(np.abs(mid) * 2.0 ** -8, np.abs(pw), None, 1, 1, 1, 0).max() * 0.25
+    tol = 2.0 ** -8 * max(1.0, float(np.abs(want).max())) + slack
+    err = np.abs(out.float().cpu().numpy() - want)
+    assert err.max() <= tol, (err.max(), tol, np.unravel_index(err.argmax(), err.shape))
