@@ -170,6 +170,8 @@ def classify_step(desc):
     layer, is_dw, h, w, cin, cout, k, stride, dil, tc = desc
     if tc == 2:
         return "sep_fused_dw3x3_pw1x1"
+    if tc == 4:
+        return "head_pair_fused_1x1_1x1"
     if tc == 3:
         return None              # pointwise half of a fused separable layer: no launch of its own
     if is_dw:
@@ -315,6 +317,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 oh, ow = -(-d[2] // d[7]), -(-d[3] // d[7])
                 fl += fl2
                 by = 2.0 * (d[2] * d[3] * d[4] + oh * ow * descs[i + 1][5]) * batch
+            if d[9] == 4:        # fused head pair: flops of the four 1x1 convs; bytes = shared input + two narrow outputs
+                fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
+                by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
             c["ms"] += ms
             c["flops"] += fl
             c["bytes"] += by
@@ -324,7 +329,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dc = classes[dom]
         # a fused separable layer is bounded by whichever of the two rooflines is slower for its shape mix:
         # report it against the tensor roofline when its tensor time exceeds its HBM time
-        tensor_bound = dom.startswith("gemm") or (dom.startswith("sep") and
+        tensor_bound = dom.startswith("gemm") or dom.startswith("head") or (dom.startswith("sep") and
                                                   dc["flops"] / (peaks["bf16_tflops_sustained"] * 1e12) >
                                                   dc["bytes"] / (peaks["hbm_gbs"] * 1e9))
         if tensor_bound:
@@ -354,6 +359,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     if d[9] == 2:
                         fl += step_work(descs[i + 1], batch)[0]
                         by = 2.0 * (d[2] * d[3] * d[4] + d[2] * d[3] * descs[i + 1][5]) * batch
+                    if d[9] == 4:
+                        fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
+                        by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
                     fh.write(json.dumps({"layer": d[0], "kind": classify_step(d), "in_hw": [d[2], d[3]], "cin": d[4],
                                          "cout": descs[i + 1][5] if d[9] == 2 else d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
                                          "tflops": round(fl / (ms * 1e-3) / 1e12, 1),

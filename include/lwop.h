@@ -59,6 +59,7 @@ extern "C" {
 /* lwop_create flags */
 #define LWOP_FLAG_NO_GRAPH      1u /* launch kernels directly instead of replaying a CUDA graph */
 #define LWOP_FLAG_NO_FUSE_SEP   2u /* separable layers as two kernels (depthwise, then 1x1 GEMM) instead of the fused one */
+#define LWOP_FLAG_NO_FUSE_HEADS 4u /* the 2-layer head pairs as four GEMM launches instead of one back-to-back kernel */
 
 /* network constants (reference src/train_config.py:25-26,31) */
 #define LWOP_NUM_JOINTS   14
@@ -190,6 +191,15 @@ int lwop_separable_conv2d(lwop_handle *h, int mode, const void *in_dev, int batc
                           const float *dw_w_dev, const float *pw_w_dev, const float *bias_dev, int cout,
                           int dilation, int act, const void *residual_dev, void *out_dev, void *stream);
 
+/* Two 2-layer 1x1-conv heads on one input, as ONE kernel (lightweight_openpose.py:32-35 and :43-46):
+ *   out_a = (relu(x W1a^T + b1a)) W2a^T + b2a   [M][14],   out_b = (relu(x W1b^T + b1b)) W2b^T + b2b   [M][26].
+ * x_dev bf16 [M][128]; weights float32 on the device: w1 [hidden][128], b1 [hidden], w2a [14][hidden], b2a [14],
+ * w2b [26][hidden], b2b [26]; hidden in {128, 512}; outputs float32. */
+int lwop_head_pair(lwop_handle *h, const void *x_dev, long long m, int hidden,
+                   const float *w1a_dev, const float *b1a_dev, const float *w2a_dev, const float *b2a_dev,
+                   const float *w1b_dev, const float *b1b_dev, const float *w2b_dev, const float *b2b_dev,
+                   float *out_a_dev, float *out_b_dev, void *stream);
+
 /* output size of a 'same' conv: ceil(in / stride) */
 int lwop_same_out(int in, int stride);
 
@@ -199,7 +209,8 @@ uint32_t lwop_crc32c(const void *data, size_t nbytes);
 /* Layer program introspection and per-kernel timing (bench.py's live roofline).
  * lwop_step_desc fills out[10] = {layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, kernel} with
  * kernel 0 = CUDA-core kernel, 1 = tcgen05 GEMM, 2 = fused depthwise+pointwise tcgen05 kernel (this depthwise step
- * and the pointwise step after it), 3 = no launch (the pointwise half absorbed into the previous step).
+ * and the pointwise step after it), 3 = no launch (absorbed into an earlier fused step), 4 = fused head pair
+ * (this step and the three after it: two 2-layer 1x1 heads as back-to-back GEMMs).
  * lwop_profile_forward runs one forward WITHOUT the CUDA graph, bracketing every
  * kernel with CUDA events on `stream`, synchronises and writes the per-step
  * durations in milliseconds to step_ms[lwop_num_steps()]. */

@@ -23,6 +23,7 @@ ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DT_F32, DT_BF16 = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_NO_FUSE_SEP = 2
+FLAG_NO_FUSE_HEADS = 4
 NUM_JOINTS, NUM_PAFS, NUM_LIMBS = 14, 26, 13
 MAX_PEAKS, MAX_JOINTS, MAX_PERSONS, COUNTS = 128, 1792, 128, 32
 
@@ -63,6 +64,7 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "lwop_depthwise3x3": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "lwop_separable_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lwop_head_pair": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lwop_same_out": (_i, [_i, _i]),
     "lwop_crc32c": (C.c_uint32, [_vp, _sz]),
     "lwop_launch_count": (C.c_longlong, [_vp, _i]),

@@ -177,20 +177,23 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        // The whole warp walks the (warp-uniform) tile schedule and waits on the barriers; one elected lane issues
+        // the MMAs and commits.  Uniform control flow keeps descriptors and barrier addresses in uniform registers,
+        // so consecutive tcgen05.mma instructions issue back to back.
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + L::kABytes;
+                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + L::kABytes;
+                if (elect_one()) {
                     const uint64_t db = make_kmajor_desc<KSWZ>(sb);
 #pragma unroll
                     for (int hm = 0; hm < MT; ++hm) {
@@ -205,11 +208,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     // frees the smem slot when these MMAs retire -- in every CTA that writes into it
                     if (CLUSTER > 1) umma_commit_multicast(&empty_bar[stage], kMask);
                     else umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kEpilogueWarp0) {
         // ===================== epilogue =====================

@@ -1,0 +1,455 @@
+// Fused head pair: two 2-layer 1x1-conv heads that share one input, as ONE kernel.
+//
+//   hidden_a = relu(X * W1a^T + b1a)   heat = hidden_a * W2a^T + b2a      (14 channels)
+//   hidden_b = relu(X * W1b^T + b1b)   paf  = hidden_b * W2b^T + b2b      (26 channels)
+//
+// Reference: the initial-stage heads conv(128->512)+conv(512->14) and conv(128->512)+conv(512->26)
+// (src/lightweight_openpose.py:32-35, concatenated at :36) and the refinement-stage heads
+// conv(128->128)+conv(128->14|26) (:43-46), all tf.layers.conv2d 1x1 + bias (+ReLU on the first of each pair,
+// src/net_factory.py:4-12).  The wide hidden tensors (2 x [M,512] for the initial stage) never leave the SM:
+// back-to-back GEMMs on the 5th-generation tensor cores.
+//
+// CTA tile = 128 pixels (rows of the flattened [M, 128] input).  The stacked first layer (N1 = 2*K2 hidden
+// channels) is walked in passes of 128 columns:
+//   MMA1(p)   acc1[p&1] (TMEM, 128 columns)  = X[128x128] * W1[p-th 128 rows]^T          (K = 128)
+//   epilogue-1 (group p&1, 4 warps): tcgen05.ld -> +bias -> ReLU -> bf16 -> written as a K-major 128B-swizzled
+//             A operand into shared memory buffer A2[p&1] (generic-proxy stores released through an mbarrier;
+//             the MMA thread crosses to the async proxy with fence.proxy.async after its acquire)
+//   MMA2(p)   acc2_head (TMEM, 16 or 32 columns) += A2[p&1][128x128] * W2_head[:, p-th K slice]^T
+// so MMA1(p+1) overlaps epilogue-1(p), and the two epilogue groups alternate passes.
+//   epilogue-2 (group 0): acc2 -> +bias -> fp32 maps and/or the bf16 concat buffer.
+// warp 0: TMA producer for X tiles and W1 chunks; warp 3: TMA producer for W2 slices; warp 1: MMA issuer;
+// warp 2: TMEM allocator; warps 4-11: epilogue groups.
+#include <stdlib.h>
+
+#include "lwop_kernels.cuh"
+
+namespace lwop {
+
+namespace {
+
+constexpr int kHpThreads = 384;
+constexpr int kHpEpiWarp0 = 4;
+constexpr int kW1Stages = 4;                  // [128 x 64] bf16 chunks, 16 KB each
+constexpr int kW2Stages = 2;                  // [<=32 x 128] bf16 slices as two 4 KB K-chunks
+constexpr int kXStages = 2;                   // [128 x 128] bf16 input tiles, 32 KB each
+
+struct HpSmem {
+    static constexpr int kXBytes = 2 * 16384;
+    static constexpr int kW1Bytes = 16384;
+    static constexpr int kW2Bytes = 8192;
+    static constexpr int kA2Bytes = 2 * 16384;
+    static constexpr int kXOff = 0;
+    static constexpr int kW1Off = kXOff + kXStages * kXBytes;
+    static constexpr int kA2Off = kW1Off + kW1Stages * kW1Bytes;
+    static constexpr int kW2Off = kA2Off + 2 * kA2Bytes;
+    static constexpr int kBarOff = kW2Off + kW2Stages * kW2Bytes;
+    static constexpr int kNumBars = 2 * kXStages + 2 * kW1Stages + 2 * kW2Stages + 4 + 4 + 2;
+    static constexpr int kBias1Off = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
+    static constexpr int kBias2Off = kBias1Off + 1024 * 4;
+    static constexpr int kTotal = kBias2Off + 64 * 4;
+};
+static_assert(HpSmem::kTotal <= 232448, "shared memory budget exceeded");
+
+struct HpParams {
+    const float *b1a, *b1b;      // [K2] each
+    const float *b2a, *b2b;      // [16], [32] (padded)
+    long long M;
+    int K2;                      // hidden width per head (512 or 128)
+    int passes;                  // 2 * K2 / 128
+    int num_m_tiles;
+    __nv_bfloat16 *cat;          // optional bf16 [M][ldc]: heat at columns cat_col_a.., paf at cat_col_b..
+    int ldc, cat_col_a, cat_col_b;
+    float *out_a, *out_b;        // optional fp32 [M][14], [M][26]
+    unsigned long long *prof;    // optional stall counters (LWOP_HEADS_PROF=1), nullptr otherwise
+};
+
+enum { HP_TOTAL = 0, HP_MMA_X, HP_MMA_ACC1_EMPTY, HP_MMA_W1, HP_MMA_A2_FULL, HP_MMA_W2, HP_MMA_ACC2_EMPTY,
+       HP_E_ACC1_FULL, HP_E_A2_EMPTY, HP_E1_WORK, HP_E_ACC2_FULL, HP_E2_WORK, HP_N };
+#define HP_WAIT(slot, stmt)                                           \
+    do {                                                              \
+        if (p.prof) {                                                 \
+            const long long _t0 = clock64();                          \
+            stmt;                                                     \
+            hp_acc[slot] += (unsigned long long)(clock64() - _t0);    \
+        } else {                                                      \
+            stmt;                                                     \
+        }                                                             \
+    } while (0)
+
+constexpr uint32_t kAcc2ColA = 256, kAcc2ColB = 288;
+
+__global__ void __launch_bounds__(kHpThreads, 1)
+head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1a,
+                 const __grid_constant__ CUtensorMap map_w1b, const __grid_constant__ CUtensorMap map_w2a,
+                 const __grid_constant__ CUtensorMap map_w2b, const HpParams p) {
+    using L = HpSmem;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    uint64_t *x_full = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
+    uint64_t *x_empty = x_full + kXStages;
+    uint64_t *w1_full = x_empty + kXStages;
+    uint64_t *w1_empty = w1_full + kW1Stages;
+    uint64_t *w2_full = w1_empty + kW1Stages;
+    uint64_t *w2_empty = w2_full + kW2Stages;
+    uint64_t *acc1_full = w2_empty + kW2Stages;      // [2]
+    uint64_t *acc1_empty = acc1_full + 2;            // [2]
+    uint64_t *a2_full = acc1_empty + 2;              // [2]
+    uint64_t *a2_empty = a2_full + 2;                // [2]
+    uint64_t *acc2_full = a2_empty + 2;
+    uint64_t *acc2_empty = acc2_full + 1;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc2_empty + 1);
+    float *bias1_s = reinterpret_cast<float *>(smem + L::kBias1Off);
+    float *bias2_s = reinterpret_cast<float *>(smem + L::kBias2Off);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = p.passes, half = P / 2;
+    unsigned long long hp_acc[HP_N];
+#pragma unroll
+    for (int i = 0; i < HP_N; ++i) hp_acc[i] = 0;
+    const long long hp_start = clock64();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w1a);
+        tma_prefetch_desc(&map_w1b);
+        tma_prefetch_desc(&map_w2a);
+        tma_prefetch_desc(&map_w2b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kXStages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < kW1Stages; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+        for (int i = 0; i < kW2Stages; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc1_full[i], 1);
+            mbar_init(&acc1_empty[i], 4);
+            mbar_init(&a2_full[i], 4);
+            mbar_init(&a2_empty[i], 1);
+        }
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_ptr);
+    for (int i = threadIdx.x; i < 2 * p.K2; i += kHpThreads) bias1_s[i] = i < p.K2 ? p.b1a[i] : p.b1b[i - p.K2];
+    for (int i = threadIdx.x; i < 48; i += kHpThreads) bias2_s[i] = i < 16 ? p.b2a[i] : p.b2b[i - 16];
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer: input tiles + first-layer weight chunks =====================
+        if (lane == 0) {
+            int xs = 0, ws = 0;
+            uint32_t xph = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                mbar_wait(&x_empty[xs], xph ^ 1);
+                mbar_arrive_expect_tx(&x_full[xs], L::kXBytes);
+                tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
+                tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
+                if (++xs == kXStages) { xs = 0; xph ^= 1; }
+                for (int pp = 0; pp < P; ++pp) {
+                    const CUtensorMap *mw = pp < half ? &map_w1a : &map_w1b;
+                    const int row0 = (pp < half ? pp : pp - half) * 128;
+                    for (int kc = 0; kc < 2; ++kc) {
+                        mbar_wait(&w1_empty[ws], wph ^ 1);
+                        mbar_arrive_expect_tx(&w1_full[ws], L::kW1Bytes);
+                        tma_load_2d(smem + L::kW1Off + ws * L::kW1Bytes, mw, &w1_full[ws], kc * 64, row0);
+                        if (++ws == kW1Stages) { ws = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA producer: second-layer weight slices =====================
+        if (lane == 0) {
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                for (int pp = 0; pp < P; ++pp) {
+                    const bool is_a = pp < half;
+                    const int k0 = (is_a ? pp : pp - half) * 128;
+                    const uint32_t bytes = is_a ? 2 * 16 * 128 : 2 * 32 * 128;
+                    mbar_wait(&w2_empty[ws], wph ^ 1);
+                    mbar_arrive_expect_tx(&w2_full[ws], bytes);
+                    unsigned char *dst = smem + L::kW2Off + ws * L::kW2Bytes;
+                    tma_load_2d(dst, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0, 0);
+                    tma_load_2d(dst + 4096, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0 + 64, 0);
+                    if (++ws == kW2Stages) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues.
+        constexpr uint32_t kIdesc1 = make_idesc_bf16(128, 128);
+        constexpr uint32_t kIdescA = make_idesc_bf16(128, 16);
+        constexpr uint32_t kIdescB = make_idesc_bf16(128, 32);
+        int xs = 0, w1s = 0, w2s = 0;
+        uint32_t xph = 0, w1ph = 0, w2ph = 0;
+        uint32_t use0 = 0, use1 = 0;       // uses of acc1 stage 0 / 1 (MMA1), phase bookkeeping
+        uint32_t useb0 = 0, useb1 = 0;     // uses of A2 buffer 0 / 1 (MMA2)
+        int local_tile = 0;
+        auto mma2 = [&](int pp) {
+            const int buf = pp & 1;
+            HP_WAIT(HP_MMA_A2_FULL, mbar_wait(&a2_full[buf], (buf ? useb1 : useb0) & 1));
+            fence_proxy_async();           // hidden activations were written with generic-proxy stores
+            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait(acc2_empty, (uint32_t)((local_tile & 1) ^ 1)));
+            HP_WAIT(HP_MMA_W2, mbar_wait(&w2_full[w2s], w2ph));
+            tcgen05_fence_after();
+            const bool is_a = pp < half;
+            const int kslice = is_a ? pp : pp - half;
+            const uint32_t d = tmem_base + (is_a ? kAcc2ColA : kAcc2ColB);
+            const uint32_t a2 = smem_u32(smem + L::kA2Off + buf * L::kA2Bytes);
+            const uint32_t w2 = smem_u32(smem + L::kW2Off + w2s * L::kW2Bytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    const uint64_t da = make_kmajor_desc<128>(a2 + kc * 16384);
+                    const uint64_t db = make_kmajor_desc<128>(w2 + kc * 4096);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
+                                     (kslice | kc | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&a2_empty[buf]);
+                umma_commit(&w2_empty[w2s]);
+            }
+            __syncwarp();
+            if (buf) ++useb1; else ++useb0;
+            if (++w2s == kW2Stages) { w2s = 0; w2ph ^= 1; }
+        };
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
+            HP_WAIT(HP_MMA_X, mbar_wait(&x_full[xs], xph));
+            const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
+            for (int pp = 0; pp < P; ++pp) {
+                const int s = pp & 1;
+                HP_WAIT(HP_MMA_ACC1_EMPTY, mbar_wait(&acc1_empty[s], ((s ? use1 : use0) & 1) ^ 1));
+                tcgen05_fence_after();
+                const uint32_t d1 = tmem_base + (uint32_t)(s * 128);
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    HP_WAIT(HP_MMA_W1, mbar_wait(&w1_full[w1s], w1ph));
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = make_kmajor_desc<128>(xa + kc * 16384);
+                        const uint64_t db = make_kmajor_desc<128>(smem_u32(smem + L::kW1Off + w1s * L::kW1Bytes));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                        umma_commit(&w1_empty[w1s]);
+                        if (kc == 1) {
+                            umma_commit(&acc1_full[s]);
+                            if (pp == P - 1) umma_commit(&x_empty[xs]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++w1s == kW1Stages) { w1s = 0; w1ph ^= 1; }
+                }
+                if (s) ++use1; else ++use0;
+                if (pp >= 1) mma2(pp - 1);
+            }
+            mma2(P - 1);
+            if (elect_one()) umma_commit(acc2_full);
+            __syncwarp();
+            if (++xs == kXStages) { xs = 0; xph ^= 1; }
+        }
+    } else if (warp >= kHpEpiWarp0) {
+        // ===================== epilogue groups =====================
+        const int q = (warp - kHpEpiWarp0) & 3;               // TMEM lane quarter == warp % 4
+        const int grp = (warp - kHpEpiWarp0) >> 2;            // owns acc1 stage / A2 buffer `grp`
+        const int row = q * 32 + lane;                        // row of the tile == TMEM lane
+        uint32_t use = 0;
+        int local_tile = 0;
+        unsigned char *a2 = smem + L::kA2Off + grp * L::kA2Bytes;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
+            for (int pp = grp; pp < P; pp += 2, ++use) {
+                HP_WAIT(HP_E_ACC1_FULL, mbar_wait(&acc1_full[grp], use & 1));
+                tcgen05_fence_after();
+                HP_WAIT(HP_E_A2_EMPTY, mbar_wait(&a2_empty[grp], (use & 1) ^ 1));   // MMA2 that read this buffer two passes ago retired
+                const long long hp_e0 = p.prof ? clock64() : 0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
+                const float *b1 = bias1_s + pp * 128;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {                 // 32 hidden columns at a time
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+                    if (c == 3) {                             // accumulator stage drained
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc1_empty[grp]);
+                    }
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(b1 + c * 32);
+                    unsigned char *dst = a2 + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = bs4[2 * j], bq = bs4[2 * j + 1];
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1])),
+                                                make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3])),
+                                                make_float2(b0.z, b0.w));
+                        const float2 s2 = fadd2(make_float2(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5])),
+                                                make_float2(bq.x, bq.y));
+                        const float2 s3 = fadd2(make_float2(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7])),
+                                                make_float2(bq.z, bq.w));
+                        uint4 o;
+                        o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
+                        o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
+                        // K-major 128B swizzle: 16-byte chunk ((c & 1) * 4 + j) XOR (row & 7)
+                        *reinterpret_cast<uint4 *>(dst + (((((c & 1) << 2) | j) ^ (row & 7)) << 4)) = o;
+                    }
+                }
+                __syncwarp();                                  // orders the lanes' stores before lane 0's release
+                if (lane == 0) mbar_arrive(&a2_full[grp]);
+                if (p.prof) hp_acc[HP_E1_WORK] += (unsigned long long)(clock64() - hp_e0);
+            }
+            if (grp == 0) {
+                // ---- epilogue-2: the two narrow linear outputs of this tile ----
+                HP_WAIT(HP_E_ACC2_FULL, mbar_wait(acc2_full, (uint32_t)(local_tile & 1)));
+                const long long hp_e2 = p.prof ? clock64() : 0;
+                tcgen05_fence_after();
+                uint32_t ra[16], rb[32];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2ColA, ra);
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2ColB, rb);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc2_empty);
+                const long long m = (long long)tile * 128 + row;
+                if (m < p.M) {
+                    float va[14], vb[26];
+#pragma unroll
+                    for (int j = 0; j < 14; ++j) va[j] = __uint_as_float(ra[j]) + bias2_s[j];
+#pragma unroll
+                    for (int j = 0; j < 26; ++j) vb[j] = __uint_as_float(rb[j]) + bias2_s[16 + j];
+                    if (p.out_a) {
+                        float2 *o = reinterpret_cast<float2 *>(p.out_a + m * 14);     // 56-byte rows: 8-byte aligned
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) o[j] = make_float2(va[2 * j], va[2 * j + 1]);
+                    }
+                    if (p.out_b) {
+                        float2 *o = reinterpret_cast<float2 *>(p.out_b + m * 26);     // 104-byte rows
+#pragma unroll
+                        for (int j = 0; j < 13; ++j) o[j] = make_float2(vb[2 * j], vb[2 * j + 1]);
+                    }
+                    if (p.cat) {
+                        __nv_bfloat16 *o = p.cat + m * p.ldc;
+#pragma unroll
+                        for (int j = 0; j < 14; ++j) o[p.cat_col_a + j] = __float2bfloat16_rn(va[j]);
+#pragma unroll
+                        for (int j = 0; j < 26; ++j) o[p.cat_col_b + j] = __float2bfloat16_rn(vb[j]);
+                    }
+                }
+                if (p.prof) hp_acc[HP_E2_WORK] += (unsigned long long)(clock64() - hp_e2);
+            }
+        }
+    }
+    if (p.prof && lane == 0 && (warp == 1 || warp == kHpEpiWarp0)) {
+        if (warp == 1) hp_acc[HP_TOTAL] = (unsigned long long)(clock64() - hp_start);
+#pragma unroll
+        for (int i = 0; i < HP_N; ++i)
+            if (hp_acc[i]) atomicAdd(p.prof + i, hp_acc[i]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+struct HeadPairPlan {
+    CUtensorMap map_x, map_w1a, map_w1b, map_w2a, map_w2b;
+    HpParams p;
+    int grid;
+};
+
+bool head_pair_supported(int cin, int hidden) { return cin == 128 && (hidden == 512 || hidden == 128); }
+
+HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t errlen) {
+    if (!gemm_driver_ready(err, errlen)) return nullptr;
+    if (!head_pair_supported(d.Cin, d.hidden)) {
+        snprintf(err, errlen, "fused head pair: unsupported Cin=%d hidden=%d", d.Cin, d.hidden);
+        return nullptr;
+    }
+    HeadPairPlan *pl = (HeadPairPlan *)calloc(1, sizeof(HeadPairPlan));
+    HpParams &p = pl->p;
+    p.b1a = d.b1a; p.b1b = d.b1b; p.b2a = d.b2a; p.b2b = d.b2b;
+    p.M = d.M;
+    p.K2 = d.hidden;
+    p.passes = 2 * d.hidden / 128;
+    p.num_m_tiles = (int)((d.M + 127) / 128);
+    p.cat = (__nv_bfloat16 *)d.cat; p.ldc = d.ldc; p.cat_col_a = d.cat_col_a; p.cat_col_b = d.cat_col_b;
+    p.out_a = d.out_a; p.out_b = d.out_b;
+    int sms = gemm_num_sms();
+    if (sms <= 0) sms = 148;
+    pl->grid = p.num_m_tiles < sms ? p.num_m_tiles : sms;
+    bool ok = true;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)d.M};
+        cuuint64_t strides[1] = {(cuuint64_t)d.lda * 2};
+        cuuint32_t box[2] = {64, 128};
+        ok = ok && encode_tiled_bf16(&pl->map_x, 2, d.in, dims, strides, box, 128, err, errlen);
+    }
+    for (int hsel = 0; hsel < 2 && ok; ++hsel) {
+        cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)d.hidden};
+        cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+        cuuint32_t box[2] = {64, 128};
+        ok = encode_tiled_bf16(hsel ? &pl->map_w1b : &pl->map_w1a, 2, hsel ? d.w1b : d.w1a, dims, strides, box, 128,
+                               err, errlen);
+    }
+    for (int hsel = 0; hsel < 2 && ok; ++hsel) {
+        cuuint64_t dims[2] = {(cuuint64_t)d.hidden, (cuuint64_t)(hsel ? 32 : 16)};
+        cuuint64_t strides[1] = {(cuuint64_t)d.hidden * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(hsel ? 32 : 16)};
+        ok = encode_tiled_bf16(hsel ? &pl->map_w2b : &pl->map_w2a, 2, hsel ? d.w2b : d.w2a, dims, strides, box, 128,
+                               err, errlen);
+    }
+    if (!ok) {
+        free(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
+void head_pair_plan_destroy(HeadPairPlan *p) { free(p); }
+
+cudaError_t head_pair_plan_launch(const HeadPairPlan *pl, cudaStream_t s, float *out_a_override, float *out_b_override) {
+    cudaError_t e = cudaFuncSetAttribute(head_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HpSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    HpParams p = pl->p;
+    if (out_a_override) p.out_a = out_a_override;
+    if (out_b_override) p.out_b = out_b_override;
+    static const bool prof = getenv("LWOP_HEADS_PROF") != nullptr;
+    if (prof) {   // debugging aid: per-role stall cycles averaged per CTA, printed to stderr (synchronises)
+        static const char *names[HP_N] = {"total", "mma:x", "mma:acc1_empty", "mma:w1", "mma:a2_full", "mma:w2",
+                                          "mma:acc2_empty", "epi0:acc1_full", "epi0:a2_empty", "epi0:e1_work",
+                                          "epi0:acc2_full", "epi0:e2_work"};
+        unsigned long long *d = nullptr, hbuf[HP_N];
+        cudaMalloc(&d, sizeof(hbuf));
+        cudaMemsetAsync(d, 0, sizeof(hbuf), s);
+        p.prof = d;
+        head_pair_kernel<<<pl->grid, kHpThreads, HpSmem::kTotal, s>>>(pl->map_x, pl->map_w1a, pl->map_w1b, pl->map_w2a,
+                                                                     pl->map_w2b, p);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        fprintf(stderr, "lwop heads prof: hidden=%d M=%lld grid=%d |", p.K2, p.M, pl->grid);
+        for (int i = 0; i < HP_N; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hbuf[i] / pl->grid);
+        fprintf(stderr, "\n");
+        return cudaGetLastError();
+    }
+    head_pair_kernel<<<pl->grid, kHpThreads, HpSmem::kTotal, s>>>(pl->map_x, pl->map_w1a, pl->map_w1b, pl->map_w2a,
+                                                                 pl->map_w2b, p);
+    return cudaGetLastError();
+}
+
+}  // namespace lwop

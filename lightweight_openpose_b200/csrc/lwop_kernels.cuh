@@ -94,6 +94,27 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen);
 void sep_plan_destroy(SepPlan *p);
 cudaError_t sep_plan_launch(const SepPlan *p, cudaStream_t s);
 
+// lwop_heads.cu -- fused pair of 2-layer 1x1 heads sharing one input (back-to-back tcgen05 GEMMs)
+struct HeadPairPlan;
+struct HeadPairDesc {
+    const void *in;              // bf16 [M][lda], Cin = 128 channels used
+    int lda, Cin;
+    long long M;
+    int hidden;                  // width of each head's hidden layer (512 or 128)
+    const void *w1a, *w1b;       // bf16 [hidden][Cin]
+    const float *b1a, *b1b;      // fp32 [hidden]
+    const void *w2a, *w2b;       // bf16 [16][hidden], [32][hidden] (rows 14.., 26.. zero)
+    const float *b2a, *b2b;      // fp32 [16], [32]
+    void *cat;                   // optional bf16 [M][ldc]: head a at columns cat_col_a.., head b at cat_col_b..
+    int ldc, cat_col_a, cat_col_b;
+    float *out_a, *out_b;        // optional fp32 [M][14], [M][26]
+};
+bool head_pair_supported(int cin, int hidden);
+HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t errlen);
+void head_pair_plan_destroy(HeadPairPlan *p);
+cudaError_t head_pair_plan_launch(const HeadPairPlan *p, cudaStream_t s, float *out_a_override = nullptr,
+                                  float *out_b_override = nullptr);
+
 // lwop_decode.cu
 struct DecodeArgs {
     const float *heat;   // [B,h,w,14]

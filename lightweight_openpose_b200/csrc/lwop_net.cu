@@ -88,6 +88,7 @@ struct PlanSet {
     std::vector<GemmPlan *> plans;   // per step (nullptr for non-GEMM steps)
     std::vector<DwPlan *> dw;        // per step (nullptr for non-depthwise steps)
     std::vector<SepPlan *> sep;      // per step: fused depthwise -> pointwise plan, stored at the depthwise step
+    std::vector<HeadPairPlan *> heads;   // per step: fused head pair (this step + the next three)
     int launches = 0;                // kernels one forward launches with these plans
 };
 
@@ -260,6 +261,8 @@ void destroy_plans(lwop_handle *h) {
             if (p) dw_plan_destroy(p);
         for (SepPlan *p : kv.second.sep)
             if (p) sep_plan_destroy(p);
+        for (HeadPairPlan *p : kv.second.heads)
+            if (p) head_pair_plan_destroy(p);
     }
     h->plan_sets.clear();
     for (auto &kv : h->graphs)
@@ -289,6 +292,27 @@ bool step_fuses_with_next(const lwop_handle *h, size_t i) {
     return sep_plan_supported(l.cin, pad_cout(l.cout), l.stride, l.dil);
 }
 
+// Steps i..i+3 = conv(128->K2)+ReLU, conv(K2->14), conv(128->K2)+ReLU, conv(K2->26) on the same input run as ONE
+// back-to-back GEMM kernel (lwop_heads.cu); LWOP_FLAG_NO_FUSE_HEADS / LWOP_NO_FUSE_HEADS=1 keep four launches.
+bool step_starts_head_pair(const lwop_handle *h, size_t i) {
+    static const bool env_off = getenv("LWOP_NO_FUSE_HEADS") != nullptr;
+    if (env_off || (h->flags & LWOP_FLAG_NO_FUSE_HEADS)) return false;
+    if (i + 3 >= h->steps.size()) return false;
+    const Step *s = &h->steps[i];
+    if (s[0].layer != 20 && s[0].layer != 39) return false;
+    for (int k = 0; k < 4; ++k)
+        if (s[k].is_dw || s[k].layer != s[0].layer + k) return false;
+    const LayerSpec &l0 = kLayers[s[0].layer], &l1 = kLayers[s[1].layer], &l2 = kLayers[s[2].layer], &l3 = kLayers[s[3].layer];
+    if (l0.k != 1 || l1.k != 1 || l2.k != 1 || l3.k != 1 || l0.cout != l2.cout || l1.cout != 14 || l3.cout != 26) return false;
+    if (s[0].in != s[2].in) return false;
+    return head_pair_supported(l0.cin, l0.cout);
+}
+int step_absorbed_by_head_pair(const lwop_handle *h, size_t i) {
+    for (size_t k = 1; k <= 3 && k <= i; ++k)
+        if (step_starts_head_pair(h, i - k)) return 1;
+    return 0;
+}
+
 int get_plans(lwop_handle *h, int batch, PlanSet **out) {
     auto it = h->plan_sets.find(batch);
     if (it != h->plan_sets.end()) {
@@ -299,6 +323,7 @@ int get_plans(lwop_handle *h, int batch, PlanSet **out) {
     ps.plans.assign(h->steps.size(), nullptr);
     ps.dw.assign(h->steps.size(), nullptr);
     ps.sep.assign(h->steps.size(), nullptr);
+    ps.heads.assign(h->steps.size(), nullptr);
     char err[256];
     auto cleanup = [&]() {
         for (GemmPlan *p : ps.plans)
@@ -307,10 +332,33 @@ int get_plans(lwop_handle *h, int batch, PlanSet **out) {
             if (p) dw_plan_destroy(p);
         for (SepPlan *p : ps.sep)
             if (p) sep_plan_destroy(p);
+        for (HeadPairPlan *p : ps.heads)
+            if (p) head_pair_plan_destroy(p);
     };
     for (size_t i = 0; i < h->steps.size(); ++i) {
         const Step &s = h->steps[i];
         const LayerSpec &l = kLayers[s.layer];
+        if (step_starts_head_pair(h, i)) {
+            const Step &s1 = h->steps[i + 1], &s3 = h->steps[i + 3];
+            HeadPairDesc d{};
+            d.in = h->arena_bf16[s.in]; d.lda = s.cin_pad; d.Cin = l.cin;
+            d.M = (long long)batch * s.H * s.W;
+            d.hidden = l.cout;
+            d.w1a = h->w_bf16[s.layer]; d.b1a = h->b_pad[s.layer];
+            d.w2a = h->w_bf16[s.layer + 1]; d.b2a = h->b_pad[s.layer + 1];
+            d.w1b = h->w_bf16[s.layer + 2]; d.b1b = h->b_pad[s.layer + 2];
+            d.w2b = h->w_bf16[s.layer + 3]; d.b2b = h->b_pad[s.layer + 3];
+            if (!s1.out_f32) {            // initial stage: heads land in the bf16 concat buffer
+                d.cat = h->arena_bf16[s1.out]; d.ldc = s1.ldo; d.cat_col_a = s1.col0; d.cat_col_b = s3.col0;
+            }
+            ps.heads[i] = head_pair_plan_create(d, err, sizeof(err));
+            if (!ps.heads[i]) {
+                cleanup();
+                return fail(h, LWOP_ERR_UNSUPPORTED, std::string("layer ") + std::to_string(s.layer) + " (fused heads): " + err);
+            }
+            i += 3;
+            continue;
+        }
         if (step_fuses_with_next(h, i)) {
             const Step &n = h->steps[i + 1];
             SepConvDesc d{};
@@ -429,6 +477,14 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
             h->launches++;
             continue;
         }
+        if (mode == LWOP_MODE_BF16 && ps->heads[i]) {
+            const Step &s1 = h->steps[i + 1];
+            float *oa = s1.out_f32 ? io.heat : io.h1, *ob = s1.out_f32 ? io.paf : io.p1;
+            CU_OK(h, head_pair_plan_launch(ps->heads[i], s, oa, ob));
+            h->launches++;
+            continue;
+        }
+        if (mode == LWOP_MODE_BF16 && step_absorbed_by_head_pair(h, i)) continue;
         if (mode == LWOP_MODE_BF16 && ps->sep[i]) {
             CU_OK(h, sep_plan_launch(ps->sep[i], s));
             h->launches++;
@@ -1061,6 +1117,52 @@ int lwop_separable_conv2d(lwop_handle *h, int mode, const void *in_dev, int batc
     return rc;
 }
 
+int lwop_head_pair(lwop_handle *h, const void *x_dev, long long m, int hidden,
+                   const float *w1a_dev, const float *b1a_dev, const float *w2a_dev, const float *b2a_dev,
+                   const float *w1b_dev, const float *b1b_dev, const float *w2b_dev, const float *b2b_dev,
+                   float *out_a_dev, float *out_b_dev, void *stream) {
+    if (!h || !x_dev || !w1a_dev || !b1a_dev || !w2a_dev || !b2a_dev || !w1b_dev || !b1b_dev || !w2b_dev || !b2b_dev ||
+        !out_a_dev || !out_b_dev)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (m < 1 || !head_pair_supported(128, hidden)) return fail(h, LWOP_ERR_UNSUPPORTED, "head pair: hidden must be 128 or 512");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_OK(h, cudaSetDevice(h->device));
+    unsigned char *buf = nullptr;
+    const size_t w1b = (size_t)hidden * 128 * 2, w2ab = (size_t)16 * hidden * 2, w2bb = (size_t)32 * hidden * 2;
+    const size_t total = 2 * w1b + w2ab + w2bb + 48 * 4;
+    CU_OK(h, cudaMalloc(&buf, total));
+    CU_OK(h, cudaMemsetAsync(buf, 0, total, s));
+    void *w1a = buf, *w1bp = buf + w1b, *w2a = buf + 2 * w1b, *w2b = buf + 2 * w1b + w2ab;
+    float *b2 = (float *)(buf + 2 * w1b + w2ab + w2bb);
+    CU_OK(h, launch_pack_bf16(w1a_dev, w1a, hidden, 128, 128, s));
+    CU_OK(h, launch_pack_bf16(w1b_dev, w1bp, hidden, 128, 128, s));
+    CU_OK(h, launch_pack_bf16(w2a_dev, w2a, 14, hidden, hidden, s));
+    CU_OK(h, launch_pack_bf16(w2b_dev, w2b, 26, hidden, hidden, s));
+    CU_OK(h, cudaMemcpyAsync(b2, b2a_dev, 14 * 4, cudaMemcpyDeviceToDevice, s));
+    CU_OK(h, cudaMemcpyAsync(b2 + 16, b2b_dev, 26 * 4, cudaMemcpyDeviceToDevice, s));
+    HeadPairDesc d{};
+    d.in = x_dev; d.lda = 128; d.Cin = 128; d.M = m; d.hidden = hidden;
+    d.w1a = w1a; d.w1b = w1bp; d.b1a = b1a_dev; d.b1b = b1b_dev;
+    d.w2a = w2a; d.w2b = w2b; d.b2a = b2; d.b2b = b2 + 16;
+    d.out_a = out_a_dev; d.out_b = out_b_dev;
+    char err[256];
+    HeadPairPlan *pl = head_pair_plan_create(d, err, sizeof(err));
+    int rc = LWOP_OK;
+    if (!pl) {
+        rc = fail(h, LWOP_ERR_UNSUPPORTED, err);
+    } else {
+        cudaError_t e = head_pair_plan_launch(pl, s);
+        h->launches += 5;
+        if (e != cudaSuccess) rc = fail(h, LWOP_ERR_CUDA, std::string("head pair launch: ") + cudaGetErrorString(e));
+        cudaError_t e2 = cudaStreamSynchronize(s);
+        if (rc == LWOP_OK && e2 != cudaSuccess)
+            rc = fail(h, LWOP_ERR_CUDA, std::string("head pair kernel: ") + cudaGetErrorString(e2));
+        head_pair_plan_destroy(pl);
+    }
+    cudaFree(buf);
+    return rc;
+}
+
 uint32_t lwop_crc32c(const void *data, size_t n) {
     std::call_once(g_crc_once, crc_init);
     const unsigned char *p = (const unsigned char *)data;
@@ -1098,6 +1200,8 @@ int lwop_step_desc(const lwop_handle *h, int step, int *out10) {
     out10[9] = step_uses_gemm(st) ? 1 : 0;
     if (step_fuses_with_next(h, (size_t)step)) out10[9] = 2;                      // fused dw -> pw kernel runs here
     else if (step > 0 && step_fuses_with_next(h, (size_t)step - 1)) out10[9] = 3; // absorbed into the previous step
+    if (step_starts_head_pair(h, (size_t)step)) out10[9] = 4;
+    else if (step_absorbed_by_head_pair(h, (size_t)step)) out10[9] = 3;
     return LWOP_OK;
 }
 

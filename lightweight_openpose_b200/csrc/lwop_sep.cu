@@ -227,7 +227,8 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp walks the warp-uniform schedule and waits; one elected lane issues (descriptors stay uniform)
+        {
             int sa = 0, sb = 0;
             uint32_t aph = 0, bph = 0;
             int local_tile = 0;
@@ -244,29 +245,32 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     // the A stage was written with ordinary (generic-proxy) stores released through a_full;
                     // this fence makes them visible to the tensor core's async-proxy reads issued below
                     fence_proxy_async();
-                    const uint64_t da = make_kmajor_desc<KSWZ>(smem_u32(smem + L::kAOff + sa * L::kABytes));
+                    const uint32_t a_addr = smem_u32(smem + L::kAOff + sa * L::kABytes);
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
                         if (NH == 2 && kb == 0) PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait(&tmem_empty[h], acc_phase ^ 1));
                         PF_WAIT(PF_MMA_B_FULL, mbar_wait(&b_full[sb], bph));
                         tcgen05_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)((NH == 1 ? acc : h) * BLOCK_N);
-                        const uint64_t db = make_kmajor_desc<KSWZ>(smem_u32(smem + L::kBOff + sb * L::kBBytes));
+                        const uint32_t b_addr = smem_u32(smem + L::kBOff + sb * L::kBBytes);
+                        if (elect_one()) {
+                            const uint64_t da = make_kmajor_desc<KSWZ>(a_addr);
+                            const uint64_t db = make_kmajor_desc<KSWZ>(b_addr);
 #pragma unroll
-                        for (int k = 0; k < kMmasPerBlock; ++k)
-                            umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
-                                         (kb | k) != 0 ? 1u : 0u);
-                        umma_commit(&b_empty[sb]);
+                            for (int k = 0; k < kMmasPerBlock; ++k)
+                                umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc,
+                                             (kb | k) != 0 ? 1u : 0u);
+                            umma_commit(&b_empty[sb]);
+                            if (h == NH - 1) umma_commit(&a_empty[sa]);
+                            if (kb == p.k_blocks - 1) {
+                                if (NH == 1) umma_commit(&tmem_full[acc]);
+                                else if (h == NH - 1) { umma_commit(&tmem_full[0]); umma_commit(&tmem_full[1]); }
+                            }
+                        }
+                        __syncwarp();
                         if (++sb == SB) { sb = 0; bph ^= 1; }
                     }
-                    umma_commit(&a_empty[sa]);
                     if (++sa == SA) { sa = 0; aph ^= 1; }
-                }
-                if (NH == 1) {
-                    umma_commit(&tmem_full[acc]);
-                } else {
-                    umma_commit(&tmem_full[0]);
-                    umma_commit(&tmem_full[1]);
                 }
             }
         }

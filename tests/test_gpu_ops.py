@@ -192,3 +192,32 @@ def test_fused_separable_kernel(eng, case):
     tol = 2.0 ** -8 * max(1.0, float(np.abs(want).max())) + slack
     err = np.abs(out.float().cpu().numpy() - want)
     assert err.max() <= tol, (err.max(), tol, np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("case", [(2 * 46 * 46, 512), (3 * 23 * 37, 128), (128, 512), (5, 128), (2 * 46 * 46 + 77, 128)])
+def test_fused_head_pair_kernel(eng, case):
+    """Two 2-layer 1x1 heads on one input as ONE back-to-back GEMM kernel (initial-stage heads 128->512->14|26,
+    refinement heads 128->128->14|26): float64 reference with the hidden activations rounded to bf16, which is
+    what the second tensor-core GEMM consumes."""
+    M, hidden = case
+    rng = np.random.default_rng(M * 7 + hidden)
+    x = bf16_round(rng.normal(size=(M, 128)))
+    w1 = [bf16_round(rng.normal(size=(hidden, 128)) / np.sqrt(128)) for _ in range(2)]
+    b1 = [rng.normal(size=(hidden,)).astype(np.float32) * 0.5 for _ in range(2)]
+    w2 = [bf16_round(rng.normal(size=(n, hidden)) / np.sqrt(hidden)) for n in (14, 26)]
+    b2 = [rng.normal(size=(n,)).astype(np.float32) for n in (14, 26)]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    xd = dev(x).to(torch.bfloat16)
+    d = [dev(a) for a in (w1[0], b1[0], w2[0], b2[0], w1[1], b1[1], w2[1], b2[1])]
+    oa = torch.full((M, 14), float("nan"), dtype=torch.float32, device="cuda")
+    ob = torch.full((M, 26), float("nan"), dtype=torch.float32, device="cuda")
+    rc = eng.lib.lwop_head_pair(eng.handle, xd.data_ptr(), M, hidden, *[t.data_ptr() for t in d], oa.data_ptr(),
+                                ob.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, eng.handle)
+    torch.cuda.synchronize()
+    for got, wa, ba, wb, bb in ((oa, w1[0], b1[0], w2[0], b2[0]), (ob, w1[1], b1[1], w2[1], b2[1])):
+        hid = np.maximum(x.astype(np.float64) @ wa.astype(np.float64).T + ba, 0.0)
+        want = bf16_round(hid).astype(np.float64) @ wb.astype(np.float64).T + bb
+        slack = (np.abs(hid) * 2.0 ** -8) @ np.abs(wb.astype(np.float64)).T * 0.25    # a few bf16 rounding flips per row
+        err = np.abs(got.cpu().numpy() - want)
+        assert (err <= 2e-4 + slack).all(), (err.max(), np.unravel_index(err.argmax(), err.shape))
