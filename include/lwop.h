@@ -130,6 +130,33 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
                 int map_h, int map_w, int img_h, int img_w, float thre1, double thre2,
                 const lwop_decode_tables *tables_dev, void *stream);
 
+/* ---- the decode stages, separately callable (what src/pose_decode.py also exports) ----
+ * Peak table layout shared by the three calls (device memory, caller-allocated):
+ *   peaks        float [batch][14][LWOP_MAX_PEAKS][4]   (x, y, score, unused) per joint channel, in kept order
+ *   peak_counts  int32 [batch][16]                      peaks per joint channel
+ * Joint ids are the running counter over (channel, peak) that NMS assigns (pose_decode.py:135,182-183). */
+#define LWOP_PEAKS_NO_REFINE 1   /* NMS(bool_refine_center=False): low-res peak snapped to the up-scaled grid (:176-182) */
+#define LWOP_PEAKS_CROSS     2   /* peak search = find_peaks (:37-49, 3x3 cross maximum filter) instead of find_peaks_v2 */
+
+/* NMS (pose_decode.py:107-185): heat_dev [batch][h][w][14] float32, `factor` = upsampFactor.  Also zeroes
+ * counts_dev [batch][LWOP_COUNTS] and sets its overflow bit (counts[b][2] & 1) if a channel has more than
+ * LWOP_MAX_PEAKS peaks. */
+int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int map_w, double factor, float thre1,
+             int mode, float *peaks_dev, int32_t *peak_counts_dev, int32_t *counts_dev, void *stream);
+
+/* find_connected_joints (pose_decode.py:188-301).  paf_dev is either the network's PAF map [batch][h][w][26]
+ * (paf_upsampled = 0: the bicubic up-sampling of decode_pose :487 is evaluated on the fly) or an already
+ * up-sampled [batch][H][W][26] map (paf_upsampled = 1, what the reference function is handed).
+ * Writes limbs_dev [batch][13][LWOP_MAX_PEAKS][5] and counts_dev[b][18 + limb_type]. */
+int lwop_find_connected_joints(lwop_handle *h, const float *paf_dev, int paf_upsampled, int batch, int map_h, int map_w,
+                               int img_h, int img_w, double thre2, const float *peaks_dev,
+                               const int32_t *peak_counts_dev, double *limbs_dev, int32_t *counts_dev, void *stream);
+
+/* joint list + group_limbs_of_same_person + keypoint table (pose_decode.py:481-482, :304-396, :403-429):
+ * fills joints / persons / keypoints of `tables_dev` and counts[b][0], [1], [3] from the peak and limb tables. */
+int lwop_group_limbs(lwop_handle *h, const float *peaks_dev, const int32_t *peak_counts_dev, int batch,
+                     const lwop_decode_tables *tables_dev, void *stream);
+
 /* Host-side result of lwop_infer_host / lwop_decode_fetch: rows of all images
  * concatenated in image order (per image: counts[b][0] joint rows, counts[b][1]
  * person / keypoint rows, counts[b][18+t] limb rows per limb type t in order). */

@@ -24,6 +24,7 @@ DT_F32, DT_BF16 = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_NO_FUSE_SEP = 2
 FLAG_NO_FUSE_HEADS = 4
+PEAKS_NO_REFINE, PEAKS_CROSS = 1, 2
 NUM_JOINTS, NUM_PAFS, NUM_LIMBS = 14, 26, 13
 MAX_PEAKS, MAX_JOINTS, MAX_PERSONS, COUNTS = 128, 1792, 128, 32
 
@@ -59,6 +60,9 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lwop_forward_u8": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "lwop_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, C.POINTER(DecodeTables), _vp]),
+    "lwop_nms": (_i, [_vp, _vp, _i, _i, _i, _d, _f, _i, _vp, _vp, _vp, _vp]),
+    "lwop_find_connected_joints": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "lwop_group_limbs": (_i, [_vp, _vp, _vp, _i, C.POINTER(DecodeTables), _vp]),
     "lwop_decode_fetch": (_i, [_vp, C.POINTER(DecodeTables), _i, C.POINTER(PackedTables), _vp]),
     "lwop_infer_host": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp]),
     "lwop_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),

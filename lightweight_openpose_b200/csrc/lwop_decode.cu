@@ -69,7 +69,7 @@ __device__ __forceinline__ int cv_round(double v) { return (int)rint(v); }
 constexpr int kRefineMax = 64;      // separable refinement handles up-sampled patches up to 64 x 64
 
 __global__ void __launch_bounds__(256)
-peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor,
+peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor, int mode,
              float *__restrict__ peaks, int *__restrict__ peak_counts, int *__restrict__ counts) {
     extern __shared__ unsigned char smem_raw[];
     const int npix = h * w;
@@ -101,6 +101,46 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
     // remaining candidate within Euclidean distance 5 of it, repeat.  "Best" = larger score, exact ties
     // towards the larger row-major index.  One block-wide arg-max per kept peak.
     int n = 0;
+    if (mode & LWOP_PEAKS_CROSS) {
+        // find_peaks (:37-49): value > thre1 and equal to the maximum over the 3x3 cross footprint (scipy
+        // maximum_filter, 'reflect' border = the border pixel itself), in np.nonzero (row-major) order.
+        __shared__ int s_cnt[256];
+        const int chunk = (npix + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int p0 = tid * chunk, p1 = min(npix, p0 + chunk);
+        auto is_peak = [&](int p) {
+            const float v = val[p];
+            if (!(v > thre1)) return false;
+            const int y = p / w, x = p - y * w;
+            float m = v;
+            if (y > 0) m = fmaxf(m, val[p - w]);
+            if (y < h - 1) m = fmaxf(m, val[p + w]);
+            if (x > 0) m = fmaxf(m, val[p - 1]);
+            if (x < w - 1) m = fmaxf(m, val[p + 1]);
+            return m == v;
+        };
+        int c = 0;
+        for (int p = p0; p < p1; ++p) c += is_peak(p) ? 1 : 0;
+        s_cnt[tid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int k = 0; k < (int)blockDim.x; ++k) { const int v = s_cnt[k]; s_cnt[k] = run; run += v; }
+            s_n = run;
+        }
+        __syncthreads();
+        int o = s_cnt[tid];
+        for (int p = p0; p < p1; ++p)
+            if (is_peak(p)) {
+                if (o < LWOP_MAX_PEAKS) s_kept[o] = p;
+                ++o;
+            }
+        n = s_n;
+        if (n > LWOP_MAX_PEAKS) {
+            if (tid == 0) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
+            n = LWOP_MAX_PEAKS;
+        }
+        __syncthreads();
+    } else
     while (true) {
         float bv = -INFINITY;
         int bp = -1;
@@ -149,6 +189,19 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
     // refinement (:148-183): bicubic up-sampling of the clipped 5x5 patch by `factor` (float32 two-pass,
     // horizontal then vertical, cv2 arithmetic), argmax = first maximum in row-major order; warp per peak.
     const double scale = 1.0 / factor;              // cv2: scale_x = 1. / inv_scale_x
+    if (mode & LWOP_PEAKS_NO_REFINE) {
+        // bool_refine_center=False (:176-182): low-res peak snapped to the up-scaled grid, score = map value
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int p = s_kept[i];
+            const int py = p / w, px = p - py * w;
+            float *o = peaks + (((long long)b * LWOP_NUM_JOINTS + ch) * LWOP_MAX_PEAKS + i) * 4;
+            o[0] = (float)floor(__dsub_rn(__dmul_rn(__dadd_rn((double)px, 0.5), factor), 0.5));
+            o[1] = (float)floor(__dsub_rn(__dmul_rn(__dadd_rn((double)py, 0.5), factor), 0.5));
+            o[2] = val[p];
+            o[3] = 0.0f;
+        }
+        return;
+    }
     for (int i = warp; i < n; i += nwarps) {
         const int p = s_kept[i];
         const int py = p / w, px = p - py * w;
@@ -276,7 +329,7 @@ __device__ __forceinline__ AxisTaps axis_taps(int d, double scale, int n) {
 // the best dst.  One warp per src joint, lanes over dst joints.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double thre2,
+limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double thre2, int direct,
              const float *__restrict__ peaks, const int *__restrict__ peak_counts, double *__restrict__ limbs,
              int *__restrict__ counts) {
     const int t = blockIdx.x, b = blockIdx.y;
@@ -300,7 +353,7 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
     for (int c = 0; c < jb; ++c) idb += pc[c];
     const float *pa = peaks + ((long long)b * LWOP_NUM_JOINTS + ja) * LWOP_MAX_PEAKS * 4;
     const float *pb = peaks + ((long long)b * LWOP_NUM_JOINTS + jb) * LWOP_MAX_PEAKS * 4;
-    const float *pafb = paf + (long long)b * h * w * LWOP_NUM_PAFS;
+    const float *pafb = paf + (long long)b * (direct ? (long long)H * W : (long long)h * w) * LWOP_NUM_PAFS;
     const int cx_ch = 2 * t, cy_ch = 2 * t + 1;                   // paf_xy_coords_per_limb (:23-24)
     const double scale_x = 1.0 / ((double)W / (double)w);         // cv2: 1. / (dsize / ssize)
     const double scale_y = 1.0 / ((double)H / (double)h);
@@ -326,6 +379,12 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
                 int X = (int)rint(fxk), Y = (int)rint(fyk);       // np.round: half to even (:260-264)
                 X = clampi(X, 0, W - 1);                          // joints are inside the frame; guard only
                 Y = clampi(Y, 0, H - 1);
+                if (direct) {       // caller passed the up-sampled PAF (find_connected_joints stage API, :267-268)
+                    const float2 v = *reinterpret_cast<const float2 *>(pafb + ((long long)Y * W + X) * LWOP_NUM_PAFS + cx_ch);
+                    s[k] = __dadd_rn(__dmul_rn((double)v.x, ux), __dmul_rn((double)v.y, uy));
+                    above += s[k] > thre2 ? 1 : 0;
+                    continue;
+                }
                 const AxisTaps tx = axis_taps(X, scale_x, w), ty = axis_taps(Y, scale_y, h);
                 float rx[4], ry[4];
 #pragma unroll
@@ -648,13 +707,44 @@ cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launch
     const int ncounts = a.B * LWOP_COUNTS;
     zero_counts_kernel<<<(ncounts + 255) / 256, 256, 0, s>>>(a.t.counts, ncounts);
     const double factor = (double)a.H / (double)a.h;              // scale = img_H / heat_H (:462)
-    peaks_kernel<<<dim3(LWOP_NUM_JOINTS, a.B), 256, smem, s>>>(a.heat, a.h, a.w, LWOP_NUM_JOINTS, a.thre1, factor,
+    peaks_kernel<<<dim3(LWOP_NUM_JOINTS, a.B), 256, smem, s>>>(a.heat, a.h, a.w, LWOP_NUM_JOINTS, a.thre1, factor, 0,
                                                                a.peaks, a.peak_counts, a.t.counts);
-    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), 128, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, a.peaks,
+    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), 128, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, 0, a.peaks,
                                                            a.peak_counts, a.t.limbs, a.t.counts);
     group_kernel<<<a.B, 32, 0, s>>>(a.peaks, a.peak_counts, a.t.limbs, a.t.counts, a.t.joints, a.t.persons,
                                     a.t.keypoints, a.work);
     if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+// ---- separately callable stages (reference NMS :107, find_connected_joints :188, group_limbs_of_same_person :304) ----
+cudaError_t launch_decode_peaks(const float *heat, int B, int h, int w, double factor, float thre1, int mode,
+                                float *peaks, int *peak_counts, int *counts, cudaStream_t s) {
+    const int npix = h * w;
+    if (npix > kMaxPixPerThread * 256) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)npix * 8 + 16;
+    if (smem > 160 * 1024) return cudaErrorInvalidValue;
+    if (smem > 16 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const int ncounts = B * LWOP_COUNTS;
+    zero_counts_kernel<<<(ncounts + 255) / 256, 256, 0, s>>>(counts, ncounts);
+    peaks_kernel<<<dim3(LWOP_NUM_JOINTS, B), 256, smem, s>>>(heat, h, w, LWOP_NUM_JOINTS, thre1, factor, mode, peaks,
+                                                             peak_counts, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_limbs(const float *paf, int upsampled, int B, int h, int w, int H, int W, double thre2,
+                                const float *peaks, const int *peak_counts, double *limbs, int *counts, cudaStream_t s) {
+    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, B), 128, 0, s>>>(paf, h, w, H, W, thre2, upsampled ? 1 : 0, peaks, peak_counts,
+                                                         limbs, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_group(const float *peaks, const int *peak_counts, const double *limbs, int *counts,
+                                double *joints, double *persons, float *keypoints, double *work, int B, cudaStream_t s) {
+    group_kernel<<<B, 32, 0, s>>>(peaks, peak_counts, limbs, counts, joints, persons, keypoints, work);
     return cudaGetLastError();
 }
 

@@ -130,6 +130,12 @@ struct DecodeArgs {
 };
 cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launches);
 size_t decode_scratch_peaks_bytes(int B);
+cudaError_t launch_decode_peaks(const float *heat, int B, int h, int w, double factor, float thre1, int mode,
+                                float *peaks, int *peak_counts, int *counts, cudaStream_t s);
+cudaError_t launch_decode_limbs(const float *paf, int upsampled, int B, int h, int w, int H, int W, double thre2,
+                                const float *peaks, const int *peak_counts, double *limbs, int *counts, cudaStream_t s);
+cudaError_t launch_decode_group(const float *peaks, const int *peak_counts, const double *limbs, int *counts,
+                                double *joints, double *persons, float *keypoints, double *work, int B, cudaStream_t s);
 size_t decode_scratch_work_bytes(int B);
 // compaction of the fixed-capacity tables: offsets[b][4] = exclusive prefix of (joints, persons, conns, 0)
 cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,

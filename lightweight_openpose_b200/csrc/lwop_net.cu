@@ -832,6 +832,46 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
     return LWOP_OK;
 }
 
+int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int map_w, double factor, float thre1,
+             int mode, float *peaks_dev, int32_t *peak_counts_dev, int32_t *counts_dev, void *stream) {
+    if (!h || !heat_dev || !peaks_dev || !peak_counts_dev || !counts_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || map_h < 1 || map_w < 1 || !(factor > 0.0)) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    if ((long long)map_h * map_w > 16384) return fail(h, LWOP_ERR_UNSUPPORTED, "heat map larger than 16384 pixels");
+    if (mode & ~(LWOP_PEAKS_NO_REFINE | LWOP_PEAKS_CROSS)) return fail(h, LWOP_ERR_INVALID, "unknown peak mode");
+    CU_OK(h, cudaSetDevice(h->device));
+    CU_OK(h, launch_decode_peaks(heat_dev, batch, map_h, map_w, factor, thre1, mode, peaks_dev, peak_counts_dev,
+                                 counts_dev, (cudaStream_t)stream));
+    h->launches += 2;
+    return LWOP_OK;
+}
+
+int lwop_find_connected_joints(lwop_handle *h, const float *paf_dev, int paf_upsampled, int batch, int map_h, int map_w,
+                               int img_h, int img_w, double thre2, const float *peaks_dev,
+                               const int32_t *peak_counts_dev, double *limbs_dev, int32_t *counts_dev, void *stream) {
+    if (!h || !paf_dev || !peaks_dev || !peak_counts_dev || !limbs_dev || !counts_dev)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || map_h < 1 || map_w < 1 || img_h < 1 || img_w < 1) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    CU_OK(h, cudaSetDevice(h->device));
+    CU_OK(h, launch_decode_limbs(paf_dev, paf_upsampled, batch, map_h, map_w, img_h, img_w, thre2, peaks_dev,
+                                 peak_counts_dev, limbs_dev, counts_dev, (cudaStream_t)stream));
+    h->launches++;
+    return LWOP_OK;
+}
+
+int lwop_group_limbs(lwop_handle *h, const float *peaks_dev, const int32_t *peak_counts_dev, int batch,
+                     const lwop_decode_tables *t, void *stream) {
+    if (!h || !peaks_dev || !peak_counts_dev || !t || !t->counts || !t->joints || !t->limbs || !t->persons || !t->keypoints)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_decode_scratch(h);
+    if (rc != LWOP_OK) return rc;
+    CU_OK(h, launch_decode_group(peaks_dev, peak_counts_dev, t->limbs, t->counts, t->joints, t->persons, t->keypoints,
+                                 h->group_work, batch, (cudaStream_t)stream));
+    h->launches++;
+    return LWOP_OK;
+}
+
 int lwop_decode_fetch(lwop_handle *h, const lwop_decode_tables *t, int batch, const lwop_packed_tables *o,
                       void *stream) {
     if (!h || !t || !o || !o->counts) return fail(h, LWOP_ERR_INVALID, "null argument");

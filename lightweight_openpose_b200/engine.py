@@ -255,6 +255,48 @@ class Engine:
                                         float(np.float32(thre1)), float(thre2), C.byref(s), self._stream()),
                    self.handle)
 
+    # -- decode stages, separately callable ------------------------------------------
+    def nms_device(self, heat, factor: float, thre1: float, mode: int = 0):
+        """Peak search + refinement on ``heat [B,h,w,14]`` (CUDA float32).  Returns the device peak table
+        ``(peaks [B,14,MAX_PEAKS,4], peak_counts [B,16], counts [B,COUNTS])``."""
+        torch = _torch()
+        B, h, w, _ = heat.shape
+        dev = heat.device
+        peaks = torch.zeros((B, _lib.NUM_JOINTS, _lib.MAX_PEAKS, 4), dtype=torch.float32, device=dev)
+        pc = torch.zeros((B, 16), dtype=torch.int32, device=dev)
+        counts = torch.zeros((B, _lib.COUNTS), dtype=torch.int32, device=dev)
+        _lib.check(self.lib.lwop_nms(self.handle, heat.data_ptr(), B, h, w, float(factor), float(np.float32(thre1)),
+                                     int(mode), peaks.data_ptr(), pc.data_ptr(), counts.data_ptr(), self._stream()),
+                   self.handle)
+        return peaks, pc, counts
+
+    def connect_device(self, paf, upsampled: bool, map_hw, img_hw, thre2: float, peaks, pc, counts):
+        """find_connected_joints on the device peak table; returns ``limbs [B,13,MAX_PEAKS,5]`` (float64)."""
+        torch = _torch()
+        B = paf.shape[0]
+        limbs = torch.zeros((B, _lib.NUM_LIMBS, _lib.MAX_PEAKS, 5), dtype=torch.float64, device=paf.device)
+        _lib.check(self.lib.lwop_find_connected_joints(self.handle, paf.data_ptr(), int(bool(upsampled)), B,
+                                                       int(map_hw[0]), int(map_hw[1]), int(img_hw[0]), int(img_hw[1]),
+                                                       float(thre2), peaks.data_ptr(), pc.data_ptr(), limbs.data_ptr(),
+                                                       counts.data_ptr(), self._stream()), self.handle)
+        return limbs
+
+    def group_device(self, peaks, pc, limbs, counts):
+        """Joint list + grouping + keypoint table from device peak / limb tables; returns device tensors
+        ``(joints [B,MAX_JOINTS,6], persons [B,MAX_PERSONS,16], keypoints [B,MAX_PERSONS,42])``; ``counts`` is updated."""
+        torch = _torch()
+        B = peaks.shape[0]
+        if B > self.max_batch:
+            raise ValueError("batch exceeds engine capacity")
+        dev = peaks.device
+        joints = torch.zeros((B, _lib.MAX_JOINTS, 6), dtype=torch.float64, device=dev)
+        persons = torch.zeros((B, _lib.MAX_PERSONS, 16), dtype=torch.float64, device=dev)
+        kp = torch.zeros((B, _lib.MAX_PERSONS, 42), dtype=torch.float32, device=dev)
+        t = _lib.DecodeTables(counts.data_ptr(), joints.data_ptr(), limbs.data_ptr(), persons.data_ptr(), kp.data_ptr())
+        _lib.check(self.lib.lwop_group_limbs(self.handle, peaks.data_ptr(), pc.data_ptr(), B, C.byref(t), self._stream()),
+                   self.handle)
+        return joints, persons, kp
+
     def fetch(self, batch: int) -> BatchResult:
         _, s = self._device_tables()
         hst = self._host_tables(batch)

@@ -111,39 +111,158 @@ def decode_pose(img_orig, param, heatmaps, pafs):
     return canvas, joint_list, persons, res.joints
 
 
-def NMS(param, heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False):
-    """Per joint type an ``(n, 5)`` float64 array ``(x, y, score, id, 0)`` (reference :107-185),
-    computed by the CUDA peak kernel (greedy radius-5 search of ``find_peaks_v2`` +
-    bicubic patch refinement)."""
-    if not bool_refine_center or bool_gaussian_filt:
-        raise NotImplementedError("only the reference's default flags (refine centre, no Gaussian filter) "
-                                  "are on the GPU path")
-    h, w = heatmaps.shape[0], heatmaps.shape[1]
-    Hf = h * float(upsampFactor)
-    if abs(Hf - round(Hf)) > 1e-9:
-        raise NotImplementedError("upsampFactor * map height must be an integer frame height")
-    H, W = int(round(Hf)), int(round(w * float(upsampFactor)))
+def _heat_to_dev(heatmaps):
     torch = _torch()
-    paf0 = torch.zeros((1, h, w, 2 * NUM_LIMBS), dtype=torch.float32, device="cuda")
-    res = decode_pose_batch((H, max(W, w)), param, np.asarray(heatmaps)[None] if isinstance(heatmaps, np.ndarray)
-                            else heatmaps[None], paf0)[0]
-    out = []
-    jl = res.joint_list
-    for j in range(NUM_JOINTS):
-        rows = jl[jl[:, 5] == j][:, :5] if jl.size else np.zeros((0, 5))
-        out.append(np.ascontiguousarray(rows))
+    engine.require_gpu(0)
+    if isinstance(heatmaps, np.ndarray):
+        heatmaps = torch.from_numpy(np.ascontiguousarray(heatmaps, dtype=np.float32))
+    return heatmaps.to(torch.device("cuda", 0), dtype=torch.float32).contiguous()
+
+
+def _check_overflow(counts) -> None:
+    if int((counts[:, 2] & 1).max()) != 0:
+        raise _lib.LwopError(_lib.ERR_OVERFLOW, f"more than {_lib.MAX_PEAKS} peaks in one joint channel")
+
+
+def _peak_lists(peaks, pc, n_channels=NUM_JOINTS):
+    """Device peak table of ONE image -> the reference's list of ``(n, 5)`` float64 arrays
+    ``(x, y, score, id, 0)`` per joint type, ids = running counter (reference :135,182-183)."""
+    pk = peaks[0].cpu().numpy()
+    cnt = pc[0].cpu().numpy()
+    out, uid = [], 0
+    for j in range(n_channels):
+        n = int(cnt[j])
+        rows = np.zeros((n, 5), dtype=np.float64)
+        rows[:, :3] = pk[j, :n, :3]
+        rows[:, 3] = np.arange(uid, uid + n)
+        uid += n
+        out.append(rows)
     return out
 
 
-def find_peaks_v2(param, img):
-    """``[[x, y], ...]`` of the greedy radius-5 peak search (reference :52-76), via the CUDA kernel."""
-    img = np.asarray(img, dtype=np.float32)
-    maps = np.zeros(img.shape + (NUM_JOINTS,), dtype=np.float32)
+def NMS(param, heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=False):
+    """Per joint type an ``(n, 5)`` float64 array ``(x, y, score, id, 0)`` (reference :107-185), computed by
+    the CUDA peak kernel: greedy radius-5 search of ``find_peaks_v2`` (:146) and, with ``bool_refine_center``,
+    the bicubic refinement of the clipped 5x5 patch (:149-175); without it the low-res peak snapped to the
+    up-scaled grid (:176-182).  The optional Gaussian smoothing of the patch (:163-164, off in every reference
+    caller) is not implemented."""
+    if bool_gaussian_filt:
+        raise NotImplementedError("bool_gaussian_filt=True (scipy gaussian_filter on the up-sampled patch) is not on "
+                                  "the GPU path; the reference never enables it")
+    heat = _heat_to_dev(heatmaps)
+    if heat.dim() != 3 or heat.shape[-1] != NUM_JOINTS:
+        raise ValueError("heatmaps must be [h, w, 14]")
+    h, w = int(heat.shape[0]), int(heat.shape[1])
+    e = _decode_engine(max(16, h), max(16, w), 1)
+    mode = 0 if bool_refine_center else _lib.PEAKS_NO_REFINE
+    peaks, pc, counts = e.nms_device(heat[None], float(upsampFactor), float(param['thre1']), mode)
+    _check_overflow(counts.cpu().numpy())
+    return _peak_lists(peaks, pc)
+
+
+def _single_channel_peaks(param, img, mode):
+    torch = _torch()
+    img = _heat_to_dev(np.asarray(img, dtype=np.float32) if not hasattr(img, "device") else img)
+    if img.dim() != 2:
+        raise ValueError("img must be a 2d map")
+    maps = torch.full(tuple(img.shape) + (NUM_JOINTS,), -np.inf, dtype=torch.float32, device=img.device)
     maps[:, :, 0] = img
-    rows = NMS_lowres(param, maps)[0]
-    return rows[:, :2].astype(np.int64)
+    h, w = int(img.shape[0]), int(img.shape[1])
+    e = _decode_engine(max(16, h), max(16, w), 1)
+    peaks, pc, counts = e.nms_device(maps[None], 1.0, float(param['thre1']), mode | _lib.PEAKS_NO_REFINE)
+    _check_overflow(counts.cpu().numpy())
+    n = int(pc[0, 0])
+    return peaks[0, 0, :n, :2].cpu().numpy().astype(np.int64)
 
 
-def NMS_lowres(param, heatmaps):
-    """Peaks at map resolution (factor 1: the 'patch refinement' of a 1x patch is the identity)."""
-    return NMS(param, heatmaps, 1.0)
+def find_peaks_v2(param, img):
+    """``[[x, y], ...]`` of the greedy radius-5 peak search, best first (reference :52-76)."""
+    return _single_channel_peaks(param, img, 0)
+
+
+def find_peaks(param, img):
+    """``[[x, y], ...]`` of the local maxima over the 3x3 cross footprint above ``thre1`` in row-major order
+    (reference :37-49; unused by the reference's own NMS, kept for API completeness)."""
+    return _single_channel_peaks(param, img, _lib.PEAKS_CROSS)
+
+
+def _peak_table_from_lists(joint_list_per_joint_type, dev):
+    """Reference-shaped list of 14 ``(n, >=3)`` arrays -> device peak table of one image.  Joint ids must be
+    the running counter NMS assigns; they are re-derived from the per-type counts on the device."""
+    torch = _torch()
+    pk = np.zeros((1, NUM_JOINTS, _lib.MAX_PEAKS, 4), dtype=np.float32)
+    pc = np.zeros((1, 16), dtype=np.int32)
+    uid = 0
+    for j, rows in enumerate(joint_list_per_joint_type):
+        rows = np.asarray(rows, dtype=np.float64).reshape(-1, 5) if len(rows) else np.zeros((0, 5))
+        n = rows.shape[0]
+        if n > _lib.MAX_PEAKS:
+            raise _lib.LwopError(_lib.ERR_OVERFLOW, f"more than {_lib.MAX_PEAKS} joints of type {j}")
+        if n and not np.array_equal(rows[:, 3], np.arange(uid, uid + n)):
+            raise ValueError("joint ids must be the running counter assigned by NMS (pose_decode.py:135,182-183)")
+        pk[0, j, :n, :3] = rows[:, :3]
+        pc[0, j] = n
+        uid += n
+    return torch.from_numpy(pk).to(dev), torch.from_numpy(pc).to(dev)
+
+
+def find_connected_joints(param, paf_upsamp, joint_list_per_joint_type, num_intermed_pts=10, max_dist_thresh=1,
+                          max_paf_score_thresh=0.7):
+    """Per limb type an ``(n, 5)`` float64 array ``(src_id, dst_id, score, i, j)`` -- or ``[]`` when either joint
+    list is empty -- exactly as the reference returns (:188-301).  ``paf_upsamp`` is the PAF map already
+    up-sampled to the frame ``[H, W, 26]`` (what ``decode_pose`` hands over, :487,493)."""
+    if num_intermed_pts != 10 or max_dist_thresh != 1:
+        raise NotImplementedError("the CUDA limb kernel implements the reference defaults "
+                                  "(num_intermed_pts=10, max_dist_thresh=1)")
+    torch = _torch()
+    engine.require_gpu(0)
+    dev = torch.device("cuda", 0)
+    paf = paf_upsamp
+    if isinstance(paf, np.ndarray):
+        paf = torch.from_numpy(np.ascontiguousarray(paf, dtype=np.float32))
+    paf = paf.to(dev, dtype=torch.float32).contiguous()
+    if paf.dim() != 3 or paf.shape[-1] != 2 * NUM_LIMBS:
+        raise ValueError("paf_upsamp must be [H, W, 26]")
+    H, W = int(paf.shape[0]), int(paf.shape[1])
+    peaks, pc = _peak_table_from_lists(joint_list_per_joint_type, dev)
+    counts = torch.zeros((1, _lib.COUNTS), dtype=torch.int32, device=dev)
+    e = _decode_engine(max(16, H), max(16, W), 1)
+    limbs = e.connect_device(paf[None], True, (H, W), (H, W), float(param['thre2']), peaks, pc, counts)
+    lim, cnt = limbs[0].cpu().numpy(), counts[0].cpu().numpy()
+    out = []
+    for t, (a, b) in enumerate(joint_to_limb_heatmap_relationship):
+        if len(joint_list_per_joint_type[a]) == 0 or len(joint_list_per_joint_type[b]) == 0:
+            out.append([])
+        else:
+            out.append(np.array(lim[t, :int(cnt[18 + t])], copy=True))
+    return out
+
+
+def group_limbs_of_same_person(connected_limbs, joint_list):
+    """``(P, 16)`` float64 person table (``(0,)`` when nobody is found) from the limb connections and the
+    flattened ``(N, 6)`` joint list (reference :304-396), by the CUDA grouping kernel."""
+    torch = _torch()
+    engine.require_gpu(0)
+    dev = torch.device("cuda", 0)
+    jl = np.asarray(joint_list, dtype=np.float64)
+    per_type = [np.zeros((0, 5))] * NUM_JOINTS
+    if jl.size:
+        jl = jl.reshape(-1, 6)
+        per_type = [jl[jl[:, 5] == j][:, :5] for j in range(NUM_JOINTS)]
+    peaks, pc = _peak_table_from_lists(per_type, dev)
+    lim = np.zeros((1, NUM_LIMBS, _lib.MAX_PEAKS, 5), dtype=np.float64)
+    counts = np.zeros((1, _lib.COUNTS), dtype=np.int32)
+    for t, rows in enumerate(connected_limbs):
+        rows = np.asarray(rows, dtype=np.float64).reshape(-1, 5) if len(rows) else np.zeros((0, 5))
+        if rows.shape[0] > _lib.MAX_PEAKS:
+            raise _lib.LwopError(_lib.ERR_OVERFLOW, f"more than {_lib.MAX_PEAKS} connections of limb type {t}")
+        lim[0, t, :rows.shape[0]] = rows
+        counts[0, 18 + t] = rows.shape[0]
+    limbs_d, counts_d = torch.from_numpy(lim).to(dev), torch.from_numpy(counts).to(dev)
+    e = _decode_engine(16, 16, 1)
+    _, persons, _ = e.group_device(peaks, pc, limbs_d, counts_d)
+    c = counts_d[0].cpu().numpy()
+    if c[2] & 2:
+        raise _lib.LwopError(_lib.ERR_OVERFLOW, f"more than {_lib.MAX_PERSONS} persons")
+    n = int(c[1])
+    return np.array(persons[0, :n].cpu().numpy(), copy=True) if n else np.array([])

@@ -149,12 +149,29 @@ def greedy_radius_peaks(channel: np.ndarray, thre1: float) -> np.ndarray:
     return np.stack([xs[kept], ys[kept]], axis=1).astype(np.int64)   # [x, y] (:72-75)
 
 
+def cross_peaks(channel: np.ndarray, thre1: float) -> np.ndarray:
+    """pose_decode.py:37-49 (find_peaks, unused by the reference's NMS): pixels above ``thre1`` equal to the
+    maximum over the 3x3 cross footprint (scipy ``maximum_filter`` with ``generate_binary_structure(2, 1)``,
+    default 'reflect' border: the mirrored neighbour of a border pixel is the pixel itself), as
+    ``[[x, y], ...]`` in ``np.nonzero`` (row-major) order."""
+    ch = np.asarray(channel)
+    m = ch.copy()
+    m[1:, :] = np.maximum(m[1:, :], ch[:-1, :])
+    m[:-1, :] = np.maximum(m[:-1, :], ch[1:, :])
+    m[:, 1:] = np.maximum(m[:, 1:], ch[:, :-1])
+    m[:, :-1] = np.maximum(m[:, :-1], ch[:, 1:])
+    ys, xs = np.nonzero((m == ch) & (ch > thre1))
+    return np.stack([xs, ys], axis=1).astype(np.int64).reshape(-1, 2)
+
+
 # ----------------------------------------------------------------------------
 # D2: patch refinement -- pose_decode.py:107-185 (NMS) + :80-104
 # ----------------------------------------------------------------------------
-def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: bool = True) -> List[np.ndarray]:
+def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: bool = True,
+                 refine: bool = True) -> List[np.ndarray]:
     """Per joint type an array [n, 5] float64 of ``(x, y, score, id, 0)`` at
-    input-image resolution; ``id`` counts peaks over channels then peaks."""
+    input-image resolution; ``id`` counts peaks over channels then peaks.
+    ``refine=False`` is ``NMS(bool_refine_center=False)`` (:176-182)."""
     h, w = heatmaps.shape[:2]
     per_type: List[np.ndarray] = []
     next_id = 0
@@ -163,6 +180,11 @@ def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: boo
         pk = greedy_radius_peaks(ch, thre1)
         rows = np.zeros((len(pk), 5), dtype=np.float64)
         for i, (px, py) in enumerate(pk):
+            if not refine:
+                rows[i] = (math.floor((px + 0.5) * factor - 0.5), math.floor((py + 0.5) * factor - 0.5),
+                           ch[py, px], next_id, 0)
+                next_id += 1
+                continue
             x0, y0 = max(0, px - PATCH_HALF), max(0, py - PATCH_HALF)          # (:150)
             x1, y1 = min(w - 1, px + PATCH_HALF), min(h - 1, py + PATCH_HALF)  # (:151-152)
             up = _resize_patch(ch[y0:y1 + 1, x0:x1 + 1], factor, use_cv2)      # (:156-158)

@@ -108,3 +108,57 @@ def test_forward_then_decode_end_to_end():
     res8 = eng.infer_host(u8, mode="bf16")
     for a, b in zip(res16, res8):
         assert np.array_equal(a.joint_list, b.joint_list)
+
+
+def _lists_equal(got, want, tol=1e-5):
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        a, b = np.asarray(a, dtype=np.float64).reshape(-1, 5), np.asarray(b, dtype=np.float64).reshape(-1, 5)
+        assert a.shape == b.shape
+        if a.size:
+            assert np.array_equal(a[:, [0, 1, 3, 4]], b[:, [0, 1, 3, 4]])      # integer fields exact
+            assert np.abs(a[:, 2] - b[:, 2]).max() <= tol
+
+
+@pytest.mark.parametrize("spec", [(500, 3, 368, 368), (501, 12, 368, 656), (502, 1, 256, 256), (503, 0, 368, 368)])
+def test_decode_stage_functions_match_oracle(spec):
+    """The separately importable stages of the reference module (NMS, find_peaks, find_peaks_v2,
+    find_connected_joints, group_limbs_of_same_person), each through its own C-ABI entry."""
+    seed, persons, H, W = spec
+    if persons:
+        heat, paf, _ = synth.synth_scene(seed, persons, H, W, noise=0.05)
+    else:
+        heat = np.zeros((H // 8, W // 8, 14), np.float32)
+        paf = np.zeros((H // 8, W // 8, 26), np.float32)
+    factor = H / heat.shape[0]
+    per_type = pose_decode.NMS(PARAM, heat, factor)
+    want = orc.refine_peaks(heat, PARAM["thre1"], factor)
+    _lists_equal(per_type, want)
+    _lists_equal(pose_decode.NMS(PARAM, heat, factor, bool_refine_center=False),
+                 orc.refine_peaks(heat, PARAM["thre1"], factor, refine=False), tol=0.0)
+    for j in (0, 7):
+        assert np.array_equal(pose_decode.find_peaks_v2(PARAM, heat[:, :, j]).reshape(-1, 2),
+                              orc.greedy_radius_peaks(heat[:, :, j], PARAM["thre1"]))
+        assert np.array_equal(pose_decode.find_peaks(PARAM, heat[:, :, j]).reshape(-1, 2),
+                              orc.cross_peaks(heat[:, :, j], PARAM["thre1"]))
+    paf_up = orc._resize_full(paf, H, W, True)                       # what decode_pose hands over (:487)
+    limbs = pose_decode.find_connected_joints(PARAM, paf_up, want)
+    ref_limbs = orc.score_limbs(paf_up, want, PARAM["thre2"])
+    for t, (a, b) in enumerate(zip(limbs, ref_limbs)):
+        empty = len(want[pose_decode.joint_to_limb_heatmap_relationship[t][0]]) == 0 or \
+            len(want[pose_decode.joint_to_limb_heatmap_relationship[t][1]]) == 0
+        if empty:
+            assert isinstance(a, list) and a == []                  # reference returns [] here (:224-228)
+        else:
+            assert np.asarray(a).shape == b.shape
+            if b.size:
+                assert np.array_equal(np.asarray(a)[:, [0, 1, 3, 4]], b[:, [0, 1, 3, 4]])
+                assert np.abs(np.asarray(a)[:, 2] - b[:, 2]).max() <= 1e-12     # direct samples: float64 exact to rounding
+    joint_list = np.array([tuple(pk) + (jt,) for jt, pks in enumerate(want) for pk in pks])
+    got_p = pose_decode.group_limbs_of_same_person(ref_limbs, joint_list)
+    want_p = orc.group_persons(ref_limbs, joint_list)
+    assert got_p.shape == want_p.shape
+    if want_p.size:
+        assert np.array_equal(got_p[:, :14], want_p[:, :14]) and np.array_equal(got_p[:, 15], want_p[:, 15])
+        assert np.abs(got_p[:, 14] - want_p[:, 14]).max() <= 1e-9
+        assert got_p.shape[0] == persons

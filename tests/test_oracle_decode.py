@@ -102,3 +102,30 @@ def test_oracle_matches_live_reference():
                 "persons": persons_arr, "joints": joints}
         got = orc.decode_detail((H, W), param, heat, paf)
         compare_decode(got, refd)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_oracle_stage_variants_match_live_reference():
+    """find_peaks (3x3 cross filter), find_peaks_v2 and NMS(bool_refine_center=False) of the reference module
+    against the oracle's restatements -- the alternate decode modes of SURVEY.md 8(f)."""
+    import warnings
+    from lightweight_openpose_b200 import synth
+    sys.path.insert(0, "/root/reference")
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from src import pose_decode as ref
+    finally:
+        sys.path.remove("/root/reference")
+    param = {"thre1": 0.1, "thre2": 0.0}
+    for seed, persons, hw in ((700, 4, (368, 368)), (701, 9, (368, 656)), (702, 1, (256, 256))):
+        heat, _, _ = synth.synth_scene(seed, persons, hw[0], hw[1], noise=0.08)
+        for j in (0, 5, 13):
+            assert np.array_equal(np.asarray(ref.find_peaks(param, heat[:, :, j])).reshape(-1, 2),
+                                  orc.cross_peaks(heat[:, :, j], 0.1))
+            assert np.array_equal(np.asarray(ref.find_peaks_v2(param, heat[:, :, j])).reshape(-1, 2),
+                                  orc.greedy_radius_peaks(heat[:, :, j], 0.1))
+        want = ref.NMS(param, heat, 8.0, bool_refine_center=False)
+        got = orc.refine_peaks(heat, 0.1, 8.0, refine=False)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, np.asarray(b).reshape(-1, 5))
