@@ -108,6 +108,13 @@ int lwop_forward(lwop_handle *h, const float *in_dev, int batch, int mode,
 int lwop_forward_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int mode,
                     float *heat_dev, float *paf_dev, void *stream);
 
+/* Frame pre-processing of the reference drivers (test&eval/model_test.py:63-64, model_json.py:68-69):
+ * cv2.cvtColor(BGR2RGB) + cv2.resize(frame, (dst_w, dst_h)) (8-bit INTER_LINEAR, OpenCV's fixed-point scheme) on
+ * the device.  in_dev uint8 [batch][src_h][src_w][3] BGR -> out_dev uint8 [batch][dst_h][dst_w][3] RGB, which is what
+ * lwop_forward_u8 (the `/ 255.` of :65) consumes. */
+int lwop_preprocess_bgr_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int src_h, int src_w,
+                           uint8_t *out_dev, int dst_h, int dst_w, void *stream);
+
 /* Decode tables, caller-allocated device memory (sizes for `batch` images):
  *   counts    int32  [batch][LWOP_COUNTS]
  *   joints    double [batch][LWOP_MAX_JOINTS][6]   (x, y, score, id, 0, joint_type)   pose_decode.py:481-482

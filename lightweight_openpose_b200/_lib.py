@@ -59,6 +59,7 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_load_weights": (_i, [_vp, _vp, _sz]),
     "lwop_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lwop_forward_u8": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "lwop_preprocess_bgr_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "lwop_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, C.POINTER(DecodeTables), _vp]),
     "lwop_nms": (_i, [_vp, _vp, _i, _i, _i, _d, _f, _i, _vp, _vp, _vp, _vp]),
     "lwop_find_connected_joints": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),

@@ -346,6 +346,53 @@ cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStr
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Frame pre-processing of the reference drivers (test&eval/model_test.py:63-64, model_json.py:68-69):
+// cv2.cvtColor(BGR2RGB) + cv2.resize(img, (W, H)) on uint8 frames.  The resize restates OpenCV's 8-bit
+// INTER_LINEAR fixed-point scheme: source position (d + 0.5) * scale - 0.5, 11-bit coefficients
+// saturate_cast<short>(f * 2048), horizontal pass in int32, vertical pass
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.   One thread per output pixel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lin_taps(int d, double scale, int n, int &s0, int &s1, int &a0, int &a1) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.0f; }
+    if (s >= n - 1) { s = n - 1; f = 0.0f; }
+    s0 = s;
+    s1 = min(s + 1, n - 1);
+    a0 = (int)(short)__float2int_rn((1.0f - f) * 2048.0f);
+    a1 = (int)(short)__float2int_rn(f * 2048.0f);
+}
+
+__global__ void preprocess_bgr_kernel(const uint8_t *__restrict__ in, int B, int Hs, int Ws, uint8_t *__restrict__ out,
+                                      int H, int W, double scale_y, double scale_x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * H * W) return;
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int b = (int)(i / ((long long)W * H));
+    int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
+    lin_taps(x, scale_x, Ws, x0, x1, ax0, ax1);
+    lin_taps(y, scale_y, Hs, y0, y1, ay0, ay1);
+    const uint8_t *r0 = in + ((long long)b * Hs + y0) * Ws * 3, *r1 = in + ((long long)b * Hs + y1) * Ws * 3;
+    uint8_t *o = out + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = (int)r0[x0 * 3 + c] * ax0 + (int)r0[x1 * 3 + c] * ax1;     // horizontal pass, scaled by 2^11
+        const int h1 = (int)r1[x0 * 3 + c] * ax0 + (int)r1[x1 * 3 + c] * ax1;
+        const int v = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[2 - c] = (uint8_t)min(max(v, 0), 255);                                  // BGR -> RGB
+    }
+}
+
+cudaError_t launch_preprocess_bgr(const uint8_t *in, int B, int Hs, int Ws, uint8_t *out, int H, int W, cudaStream_t s) {
+    const long long n = (long long)B * H * W;
+    preprocess_bgr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, B, Hs, Ws, out, H, W, (double)Hs / H,
+                                                                      (double)Ws / W);
+    return cudaGetLastError();
+}
+
 // fp32 [rows][cols] -> bf16 [rows][cols_padded] (zero padding), used to pack weights
 __global__ void pack_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows,
                                  int cols, int cols_padded) {

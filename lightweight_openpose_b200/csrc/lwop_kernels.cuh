@@ -34,6 +34,7 @@ cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s);
 cudaError_t set_conv1_constants(const float *w_host_n27, const float *b_host);   // per device, at weight load
 cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s);
 cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStream_t s);
+cudaError_t launch_preprocess_bgr(const uint8_t *in, int B, int Hs, int Ws, uint8_t *out, int H, int W, cudaStream_t s);
 cudaError_t launch_pack_bf16(const float *src, void *dst, long long rows, int cols, int cols_padded,
                              cudaStream_t s);
 

@@ -815,6 +815,16 @@ int lwop_forward_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int mode, 
     return forward_impl(h, io, batch, mode, (cudaStream_t)stream);
 }
 
+int lwop_preprocess_bgr_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int src_h, int src_w,
+                           uint8_t *out_dev, int dst_h, int dst_w, void *stream) {
+    if (!h || !in_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    CU_OK(h, cudaSetDevice(h->device));
+    CU_OK(h, launch_preprocess_bgr(in_dev, batch, src_h, src_w, out_dev, dst_h, dst_w, (cudaStream_t)stream));
+    h->launches++;
+    return LWOP_OK;
+}
+
 int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int batch, int map_h, int map_w,
                 int img_h, int img_w, float thre1, double thre2, const lwop_decode_tables *t, void *stream) {
     if (!h || !heat_dev || !paf_dev || !t || !t->counts || !t->joints || !t->limbs || !t->persons || !t->keypoints)
