@@ -50,11 +50,21 @@ __device__ __forceinline__ void src_pos(int d, double scale, int &s, float &frac
     frac = __fsub_rn(f, fl);
 }
 
+// horizontal pass of OpenCV's resize engine (HResizeCubic): products summed left to right
 __device__ __forceinline__ float dot4(const float (&v)[4], const float (&c)[4]) {
     float r = __fmul_rn(v[0], c[0]);
     r = __fadd_rn(r, __fmul_rn(v[1], c[1]));
     r = __fadd_rn(r, __fmul_rn(v[2], c[2]));
     r = __fadd_rn(r, __fmul_rn(v[3], c[3]));
+    return r;
+}
+// vertical pass (VResizeCubic): products summed right to left -- with this pair of orders the result equals
+// cv2.resize(INTER_CUBIC, float32) bit for bit when OpenCV runs its own code (oracle/decode_oracle.py)
+__device__ __forceinline__ float dot4_rev(const float (&v)[4], const float (&c)[4]) {
+    float r = __fmul_rn(v[3], c[3]);
+    r = __fadd_rn(r, __fmul_rn(v[2], c[2]));
+    r = __fadd_rn(r, __fmul_rn(v[1], c[1]));
+    r = __fadd_rn(r, __fmul_rn(v[0], c[0]));
     return r;
 }
 
@@ -255,7 +265,7 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
                     t[r] = s_h[warp][clampi(sy - 1 + r, 0, ph - 1)][ox];
                     c[r] = s_cy[warp][oy][r];
                 }
-                const float v = dot4(t, c);
+                const float v = dot4_rev(t, c);
                 if (v > best_v) { best_v = v; best_i = d; }
             }
             __syncwarp();
@@ -277,7 +287,7 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
                     for (int k = 0; k < 4; ++k) t[k] = val[yy * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
                     rows[r] = dot4(t, cx);
                 }
-                const float v = dot4(rows, cy);
+                const float v = dot4_rev(rows, cy);
                 if (v > best_v) { best_v = v; best_i = d; }
             }
         }
@@ -400,7 +410,7 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
                     rx[r] = dot4(vx, tx.c);
                     ry[r] = dot4(vy, tx.c);
                 }
-                const double px = (double)dot4(rx, ty.c), py = (double)dot4(ry, ty.c);
+                const double px = (double)dot4_rev(rx, ty.c), py = (double)dot4_rev(ry, ty.c);
                 s[k] = __dadd_rn(__dmul_rn(px, ux), __dmul_rn(py, uy));   // intermed_paf.dot(limb_dir) (:270)
                 above += s[k] > thre2 ? 1 : 0;
             }
@@ -653,22 +663,28 @@ pack_offsets_kernel(const int *__restrict__ counts, int B, int *__restrict__ off
 
 __global__ void __launch_bounds__(128)
 pack_rows_kernel(lwop_decode_tables t, const int *__restrict__ offsets, double *__restrict__ joints_p,
-                 double *__restrict__ limbs_p, double *__restrict__ persons_p, float *__restrict__ keypoints_p) {
+                 double *__restrict__ limbs_p, double *__restrict__ persons_p, float *__restrict__ keypoints_p,
+                 long long cap_j, long long cap_l, long long cap_p) {
+    // rows that would land beyond a packed buffer's capacity are dropped; the host detects that from the counts
     const int b = blockIdx.x, tid = threadIdx.x;
     const int *cnt = t.counts + b * LWOP_COUNTS;
     const int *off = offsets + b * 4;
     const int nj = cnt[0], np = cnt[1];
     const double *js = t.joints + (long long)b * LWOP_MAX_JOINTS * 6;
-    for (int i = tid; i < nj * 6; i += blockDim.x) joints_p[(long long)off[0] * 6 + i] = js[i];
-    const double *ps = t.persons + (long long)b * LWOP_MAX_PERSONS * 16;
-    for (int i = tid; i < np * 16; i += blockDim.x) persons_p[(long long)off[1] * 16 + i] = ps[i];
-    const float *ks = t.keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
-    for (int i = tid; i < np * 42; i += blockDim.x) keypoints_p[(long long)off[1] * 42 + i] = ks[i];
+    if ((long long)off[0] + nj <= cap_j)
+        for (int i = tid; i < nj * 6; i += blockDim.x) joints_p[(long long)off[0] * 6 + i] = js[i];
+    if ((long long)off[1] + np <= cap_p) {
+        const double *ps = t.persons + (long long)b * LWOP_MAX_PERSONS * 16;
+        for (int i = tid; i < np * 16; i += blockDim.x) persons_p[(long long)off[1] * 16 + i] = ps[i];
+        const float *ks = t.keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
+        for (int i = tid; i < np * 42; i += blockDim.x) keypoints_p[(long long)off[1] * 42 + i] = ks[i];
+    }
     long long row = off[2];
     for (int l = 0; l < LWOP_NUM_LIMBS; ++l) {
         const int nc = cnt[18 + l];
         const double *ls = t.limbs + ((long long)b * LWOP_NUM_LIMBS + l) * LWOP_MAX_PEAKS * 5;
-        for (int i = tid; i < nc * 5; i += blockDim.x) limbs_p[row * 5 + i] = ls[i];
+        if (row + nc <= cap_l)
+            for (int i = tid; i < nc * 5; i += blockDim.x) limbs_p[row * 5 + i] = ls[i];
         row += nc;
     }
 }
@@ -688,9 +704,10 @@ size_t decode_scratch_peaks_bytes(int B) {
 
 cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,
                                double *limbs_packed, double *persons_packed, float *keypoints_packed,
-                               cudaStream_t s, long long *launches) {
+                               cudaStream_t s, long long *launches, long long cap_j, long long cap_l, long long cap_p) {
     pack_offsets_kernel<<<1, 1024, 0, s>>>(t.counts, B, offsets);
-    pack_rows_kernel<<<B, 128, 0, s>>>(t, offsets, joints_packed, limbs_packed, persons_packed, keypoints_packed);
+    pack_rows_kernel<<<B, 128, 0, s>>>(t, offsets, joints_packed, limbs_packed, persons_packed, keypoints_packed, cap_j,
+                                       cap_l, cap_p);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -141,6 +141,7 @@ size_t decode_scratch_work_bytes(int B);
 // compaction of the fixed-capacity tables: offsets[b][4] = exclusive prefix of (joints, persons, conns, 0)
 cudaError_t launch_decode_pack(const lwop_decode_tables &t, int B, int *offsets, double *joints_packed,
                                double *limbs_packed, double *persons_packed, float *keypoints_packed,
-                               cudaStream_t s, long long *launches);
+                               cudaStream_t s, long long *launches, long long cap_joints = (1ll << 60),
+                               long long cap_limbs = (1ll << 60), long long cap_persons = (1ll << 60));
 
 }  // namespace lwop

@@ -82,7 +82,13 @@ def _axis_table(dst: int, src: int, scale: float) -> Tuple[np.ndarray, np.ndarra
 
 def bicubic_resize_f32(src: np.ndarray, dst_h: int, dst_w: int, scale_y: float, scale_x: float) -> np.ndarray:
     """float32 two-pass bicubic (horizontal 4-tap, then vertical 4-tap) of a
-    [h, w] or [h, w, c] array, the order cv2's resize engine uses."""
+    [h, w] or [h, w, c] array, in the operation order of OpenCV's own resize engine
+    (modules/imgproc/src/resize.cpp): the horizontal pass sums its four products left to
+    right, ((v0*c0 + v1*c1) + v2*c2) + v3*c3, the vertical pass right to left,
+    ((v3*c3 + v2*c2) + v1*c1) + v0*c0, no fused multiply-adds.  With that order this
+    function equals ``cv2.resize(..., INTER_CUBIC)`` BIT FOR BIT when OpenCV runs its own
+    code (``cv2.ipp.setUseIPP(False)``); IPP-accelerated builds differ from it by 1 ulp on
+    about a third of the pixels (tests/test_oracle_decode.py pins both facts)."""
     a = np.asarray(src, dtype=np.float32)
     squeeze = a.ndim == 2
     if squeeze:
@@ -94,9 +100,9 @@ def bicubic_resize_f32(src: np.ndarray, dst_h: int, dst_w: int, scale_y: float, 
         term = a[:, xi[:, k], :] * xw[:, k][None, :, None]
         rows = term if k == 0 else (rows + term).astype(np.float32)
     out = np.zeros((dst_h, dst_w, a.shape[2]), dtype=np.float32)
-    for k in range(4):
+    for k in (3, 2, 1, 0):
         term = rows[yi[:, k], :, :] * yw[:, k][:, None, None]
-        out = term if k == 0 else (out + term).astype(np.float32)
+        out = term if k == 3 else (out + term).astype(np.float32)
     return out[:, :, 0] if squeeze else out
 
 

@@ -27,10 +27,9 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(scope="session")
-def decode_golden():
+def _load_golden(fname):
     import numpy as np
-    path = os.path.join(ROOT, "tests", "golden", "decode_golden.npz")
+    path = os.path.join(ROOT, "tests", "golden", fname)
     z = np.load(path)
     scenes = {}
     for name in z["names"]:
@@ -43,3 +42,15 @@ def decode_golden():
             "persons": z[f"{name}/persons"], "joints": z[f"{name}/joints"],
         }
     return scenes, {"thre1": float(z["thre"][0]), "thre2": float(z["thre"][1])}
+
+
+@pytest.fixture(scope="session")
+def decode_golden():
+    """Reference module with cv2 as installed (IPP-accelerated patch resize)."""
+    return _load_golden("decode_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def decode_golden_noipp():
+    """Reference module with cv2.ipp.setUseIPP(False): OpenCV's own float32 arithmetic (bit-exact target)."""
+    return _load_golden("decode_golden_noipp.npz")

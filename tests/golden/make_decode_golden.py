@@ -1,8 +1,15 @@
-"""Generates ``tests/golden/decode_golden.npz`` by running the UNMODIFIED
+"""Generates ``tests/golden/decode_golden.npz`` and ``decode_golden_noipp.npz`` by running the UNMODIFIED
 reference decoder (``/root/reference/src/pose_decode.py``) on seeded scenes.
 
 Run in the build container only (the reference tree does not exist on the GPU
 box):  ``python tests/golden/make_decode_golden.py``
+
+Two files because the reference's ``cv2.resize`` is not one function: OpenCV builds with the (binary-only)
+IPP accelerator route the single-channel 5x5 patch resize to IPP, whose float32 results differ from OpenCV's
+own C++ code by 1 ulp on ~25% of the pixels (the 26-channel PAF resize takes OpenCV's own code either way).
+``decode_golden.npz`` is the module run with cv2 as installed (IPP on); ``decode_golden_noipp.npz`` is the same
+module after ``cv2.ipp.setUseIPP(False)`` = OpenCV's own arithmetic, which the oracle restatement and the CUDA
+kernels reproduce bit for bit (scores included).
 
 For every scene the file stores the inputs (heatmaps, pafs, image size,
 thresholds) and the reference outputs: ``joint_list`` (N,6) f64, the 13 limb
@@ -40,10 +47,11 @@ def single_peak_scene():
     return heat, paf
 
 
-def main():
+def main(use_ipp=True, fname="decode_golden.npz"):
     warnings.simplefilter("ignore")
     import cv2
     cv2.setNumThreads(1)
+    cv2.ipp.setUseIPP(use_ipp)
     from src import pose_decode as ref            # the reference module itself
 
     param = {"thre1": 0.1, "thre2": 0.0}
@@ -79,10 +87,11 @@ def main():
     out["names"] = np.array(names)
     out["thre"] = np.array([param["thre1"], param["thre2"]])
     out["versions"] = np.array([cv2.__version__, np.__version__, str(cv2.ipp.useIPP())])
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "decode_golden.npz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), fname)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path))
 
 
 if __name__ == "__main__":
-    main()
+    main(True, "decode_golden.npz")
+    main(False, "decode_golden_noipp.npz")

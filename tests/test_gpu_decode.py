@@ -27,6 +27,15 @@ def test_decode_matches_reference_golden(decode_golden):
         compare_decode(_as_dict(res), sc)
 
 
+def test_decode_bit_exact_vs_reference_without_ipp(decode_golden_noipp):
+    """Against the reference module run on OpenCV's own float32 arithmetic (IPP off): everything exact,
+    float scores included."""
+    scenes, param = decode_golden_noipp
+    for name, sc in scenes.items():
+        res = pose_decode.decode_pose_batch(sc["hw"], param, sc["heat"][None], sc["paf"][None])[0]
+        compare_decode(_as_dict(res), sc, float_tol=0.0, f64_tol=1e-14)
+
+
 def test_decode_pose_signature_and_types(decode_golden):
     scenes, param = decode_golden
     sc = scenes["three_368"]
