@@ -195,7 +195,21 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
                     float thre1, double thre2, const lwop_packed_tables *out_host,
                     float *heat_host, float *paf_host, void *stream);
 
-/* Tunables: "chunk" = images per pipeline stage of lwop_infer_host (default 64). */
+/* Asynchronous form of lwop_infer_host, for callers that keep batches in flight (a serving loop): _begin enqueues
+ * upload, forward, decode, compaction and the download of the result tables into `out_host` and returns a ticket
+ * without waiting; _end(ticket) waits for that batch and reports overflow.  With two batches in flight the upload
+ * of batch k+1 overlaps the kernels of batch k.  The result tables are downloaded at the capacities given in
+ * `out_host` (the used row counts are only known afterwards, from counts); LWOP_ERR_OVERFLOW from _end means the
+ * capacities were too small for this batch: enlarge them and run the batch again.  `out_host` and `images_host`
+ * must stay valid (and should be pinned) until _end returns.  lwop_infer_host == _begin + _end. */
+#define LWOP_MAX_INFLIGHT 2
+int lwop_infer_host_begin(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode,
+                          float thre1, double thre2, const lwop_packed_tables *out_host,
+                          float *heat_host, float *paf_host, void *stream, int *ticket);
+int lwop_infer_host_end(lwop_handle *h, int ticket);
+
+/* Tunables: "chunk" = images per pipeline stage of lwop_infer_host (0 = default: 64 for float32 frames, 128 for
+ * uint8; the asynchronous entry submits the whole batch as one chunk). */
 int lwop_set_option(lwop_handle *h, const char *name, long long value);
 
 /* ---- per-op entries mirroring src/net_factory.py (unit tests, eager mode) ---- */

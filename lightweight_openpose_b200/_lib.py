@@ -66,6 +66,8 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_group_limbs": (_i, [_vp, _vp, _vp, _i, C.POINTER(DecodeTables), _vp]),
     "lwop_decode_fetch": (_i, [_vp, C.POINTER(DecodeTables), _i, C.POINTER(PackedTables), _vp]),
     "lwop_infer_host": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp]),
+    "lwop_infer_host_begin": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp, C.POINTER(_i)]),
+    "lwop_infer_host_end": (_i, [_vp, _i]),
     "lwop_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "lwop_depthwise3x3": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "lwop_separable_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

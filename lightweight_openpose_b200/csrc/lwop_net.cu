@@ -136,6 +136,7 @@ struct lwop_handle {
     int *h_offsets = nullptr;                    // pinned
     // infer_host pipeline: two slots (input staging + maps), a copy stream and events
     int chunk = 0, pipe_chunk = 0;
+    unsigned long long slot_seq = 0;
     bool pipe_ready = false;
     void *slot_in[2] = {};
     float *slot_heat[2] = {}, *slot_paf[2] = {};
@@ -143,6 +144,18 @@ struct lwop_handle {
     cudaStream_t copy_stream = nullptr, decode_stream = nullptr;
     lwop_decode_tables own_tables = {};
     int own_tables_batch = 0;
+    // batches in flight through lwop_infer_host_begin / _end: each lane owns its decode tables and packed buffers
+    struct HostLane {
+        lwop_decode_tables tables = {};
+        int *pack_offsets = nullptr;
+        double *pk_joints = nullptr, *pk_limbs = nullptr, *pk_persons = nullptr;
+        float *pk_keypoints = nullptr;
+        size_t cap_j = 0, cap_l = 0, cap_p = 0;
+        cudaEvent_t ev_ready = nullptr;
+        bool busy = false;
+        int batch = 0;
+        lwop_packed_tables out = {};
+    } lanes[LWOP_MAX_INFLIGHT];
 };
 
 namespace {
@@ -746,6 +759,19 @@ int lwop_destroy(lwop_handle *h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->decode_stream) cudaStreamDestroy(h->decode_stream);
+    for (auto &ln : h->lanes) {
+        if (ln.tables.counts) cudaFree(ln.tables.counts);
+        if (ln.tables.joints) cudaFree(ln.tables.joints);
+        if (ln.tables.limbs) cudaFree(ln.tables.limbs);
+        if (ln.tables.persons) cudaFree(ln.tables.persons);
+        if (ln.tables.keypoints) cudaFree(ln.tables.keypoints);
+        if (ln.pack_offsets) cudaFree(ln.pack_offsets);
+        if (ln.pk_joints) cudaFree(ln.pk_joints);
+        if (ln.pk_limbs) cudaFree(ln.pk_limbs);
+        if (ln.pk_persons) cudaFree(ln.pk_persons);
+        if (ln.pk_keypoints) cudaFree(ln.pk_keypoints);
+        if (ln.ev_ready) cudaEventDestroy(ln.ev_ready);
+    }
     if (h->own_tables.counts) cudaFree(h->own_tables.counts);
     if (h->own_tables.joints) cudaFree(h->own_tables.joints);
     if (h->own_tables.limbs) cudaFree(h->own_tables.limbs);
@@ -920,85 +946,125 @@ int lwop_decode_fetch(lwop_handle *h, const lwop_decode_tables *t, int batch, co
     return LWOP_OK;
 }
 
-int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
-                    double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream) {
-    if (!h || !images_host || !o) return fail(h, LWOP_ERR_INVALID, "null argument");
+namespace {
+
+int ensure_lane(lwop_handle *h, lwop_handle::HostLane &ln, const lwop_packed_tables *o) {
+    const size_t B = h->max_batch;
+    if (!ln.tables.counts) {
+        CU_OK(h, cudaMalloc(&ln.tables.counts, B * LWOP_COUNTS * sizeof(int32_t)));
+        CU_OK(h, cudaMalloc(&ln.tables.joints, B * LWOP_MAX_JOINTS * 6 * sizeof(double)));
+        CU_OK(h, cudaMalloc(&ln.tables.limbs, B * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 5 * sizeof(double)));
+        CU_OK(h, cudaMalloc(&ln.tables.persons, B * LWOP_MAX_PERSONS * 16 * sizeof(double)));
+        CU_OK(h, cudaMalloc(&ln.tables.keypoints, B * LWOP_MAX_PERSONS * 42 * sizeof(float)));
+        CU_OK(h, cudaMalloc(&ln.pack_offsets, (B + 1) * 4 * sizeof(int)));
+        CU_OK(h, cudaEventCreateWithFlags(&ln.ev_ready, cudaEventDisableTiming));
+    }
+    if (o->joints_cap > ln.cap_j) {
+        if (ln.pk_joints) cudaFree(ln.pk_joints);
+        ln.cap_j = o->joints_cap;
+        CU_OK(h, cudaMalloc(&ln.pk_joints, ln.cap_j * 6 * sizeof(double)));
+    }
+    if (o->limbs_cap > ln.cap_l) {
+        if (ln.pk_limbs) cudaFree(ln.pk_limbs);
+        ln.cap_l = o->limbs_cap;
+        CU_OK(h, cudaMalloc(&ln.pk_limbs, ln.cap_l * 5 * sizeof(double)));
+    }
+    if (o->persons_cap > ln.cap_p) {
+        if (ln.pk_persons) cudaFree(ln.pk_persons);
+        if (ln.pk_keypoints) cudaFree(ln.pk_keypoints);
+        ln.cap_p = o->persons_cap;
+        CU_OK(h, cudaMalloc(&ln.pk_persons, ln.cap_p * 16 * sizeof(double)));
+        CU_OK(h, cudaMalloc(&ln.pk_keypoints, ln.cap_p * 42 * sizeof(float)));
+    }
+    return LWOP_OK;
+}
+
+}  // namespace
+
+namespace {
+int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
+                          double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream,
+                          int *ticket, bool lone_call);
+}
+
+int lwop_infer_host_begin(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
+                          double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream,
+                          int *ticket) {
+    return infer_host_begin_impl(h, images_host, is_u8, batch, mode, thre1, thre2, o, heat_host, paf_host, stream, ticket,
+                                 false);
+}
+
+namespace {
+int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
+                          double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream,
+                          int *ticket, bool lone_call) {
+    if (!h || !images_host || !o || !o->counts || !ticket) return fail(h, LWOP_ERR_INVALID, "null argument");
     if (batch < 1 || batch > h->max_batch) return fail(h, LWOP_ERR_INVALID, "batch out of range");
+    if (!h->has_weights) return fail(h, LWOP_ERR_NO_WEIGHTS, "lwop_infer_host before lwop_load_weights");
+    int lane = -1;
+    for (int i = 0; i < LWOP_MAX_INFLIGHT; ++i)
+        if (!h->lanes[i].busy) { lane = i; break; }
+    if (lane < 0) return fail(h, LWOP_ERR_INVALID, "too many batches in flight: call lwop_infer_host_end first");
     cudaStream_t s = (cudaStream_t)stream;
     CU_OK(h, cudaSetDevice(h->device));
     // The batch is cut into chunks that flow through a two-slot pipeline: the copy stream uploads chunk
-    // k+1 while the compute stream runs forward + decode of chunk k (one CUDA graph per slot).
-    int chunk = h->chunk > 0 ? h->chunk : 64;
+    // k+1 while the compute stream runs the forward of chunk k and the decode stream decodes chunk k-1
+    // (one CUDA graph per slot).  Slots are guarded by events across calls as well, so the upload of the NEXT
+    // batch overlaps the kernels of this one when the caller keeps two batches in flight.
+    // Default chunking: the synchronous lwop_infer_host hides its own upload by cutting the batch into chunks; a
+    // batch submitted through the asynchronous entry hides its upload behind the kernels of the batch before it,
+    // so it goes through whole (fewer, larger launches).
+    int chunk = h->chunk > 0 ? h->chunk : (!lone_call ? batch : (is_u8 ? 128 : 64));
     if (chunk > batch) chunk = batch;
     if (chunk > h->max_batch) chunk = h->max_batch;
     const size_t img_elems = (size_t)h->H * h->W * 3;
     const size_t px = (size_t)h->h8 * h->w8;
-    if (!h->pipe_ready || h->pipe_chunk < chunk) {
+    if (!h->pipe_ready) {
+        const int alloc_chunk = h->max_batch;    // slots are sized for max_batch once: the chunk size may vary per call
+        CU_OK(h, cudaDeviceSynchronize());       // nothing may still use the old slots
         for (int k = 0; k < 2; ++k) {
             if (h->slot_in[k]) cudaFree(h->slot_in[k]);
             if (h->slot_heat[k]) cudaFree(h->slot_heat[k]);
             if (h->slot_paf[k]) cudaFree(h->slot_paf[k]);
-            CU_OK(h, cudaMalloc(&h->slot_in[k], (size_t)chunk * img_elems * 4));
-            CU_OK(h, cudaMalloc(&h->slot_heat[k], (size_t)chunk * px * LWOP_NUM_JOINTS * 4));
-            CU_OK(h, cudaMalloc(&h->slot_paf[k], (size_t)chunk * px * LWOP_NUM_PAFS * 4));
+            CU_OK(h, cudaMalloc(&h->slot_in[k], (size_t)alloc_chunk * img_elems * 4));
+            CU_OK(h, cudaMalloc(&h->slot_heat[k], (size_t)alloc_chunk * px * LWOP_NUM_JOINTS * 4));
+            CU_OK(h, cudaMalloc(&h->slot_paf[k], (size_t)alloc_chunk * px * LWOP_NUM_PAFS * 4));
             if (!h->ev_h2d[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
             if (!h->ev_done[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
             if (!h->ev_fwd[k]) CU_OK(h, cudaEventCreateWithFlags(&h->ev_fwd[k], cudaEventDisableTiming));
         }
-        if (!h->ev_start) CU_OK(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
         if (!h->ev_join) CU_OK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         if (!h->copy_stream) CU_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->decode_stream) CU_OK(h, cudaStreamCreateWithFlags(&h->decode_stream, cudaStreamNonBlocking));
-        h->pipe_chunk = chunk;
+        h->pipe_chunk = alloc_chunk;
         h->pipe_ready = true;
         destroy_graphs_only(h);          // slot pointers changed
     }
-    int rc = ensure_own_tables(h);
+    lwop_handle::HostLane &ln = h->lanes[lane];
+    int rc = ensure_lane(h, ln, o);
     if (rc != LWOP_OK) return rc;
     rc = ensure_decode_scratch(h);
     if (rc != LWOP_OK) return rc;
     const size_t esz = is_u8 ? 1 : 4;
-    // LWOP_TRACE=1: timing events at the pipeline's milestones, printed to stderr (debugging aid)
-    static const bool trace = getenv("LWOP_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    std::vector<std::string> tname;
-    auto mark = [&](const char *name, int k, cudaStream_t st) {
-        if (!trace) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        tev.push_back(e);
-        tname.push_back(std::string(name) + std::to_string(k));
-    };
-    // three streams: copy (H2D), `s` (forward), decode.  Slot k&1 holds chunk k's frames and maps; it is
-    // re-used by chunk k+2 once chunk k's decode (and optional map download) has finished.
     cudaStream_t ds = h->decode_stream;
-    mark("start", 0, s);
-    CU_OK(h, cudaEventRecord(h->ev_start, s));
-    CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_start, 0));
-    CU_OK(h, cudaStreamWaitEvent(ds, h->ev_start, 0));
     // chunk schedule: a half-size first chunk shortens the only upload that nothing can hide
     int k = 0;
     for (int b0 = 0, nb = 0; b0 < batch; b0 += nb, ++k) {
         nb = (k == 0 && batch > chunk && chunk >= 16) ? chunk / 2 : chunk;
         if (nb > batch - b0) nb = batch - b0;
-        const int slot = k & 1;
-        if (k >= 2) {
-            CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_fwd[slot], 0));   // frames of chunk k-2 consumed
-            CU_OK(h, cudaStreamWaitEvent(s, h->ev_done[slot], 0));               // maps of chunk k-2 decoded
-        }
+        const int slot = (int)(h->slot_seq++ & 1);                           // slots alternate ACROSS calls too
+        CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_fwd[slot], 0));   // previous frames in this slot consumed
+        CU_OK(h, cudaStreamWaitEvent(s, h->ev_done[slot], 0));               // previous maps in this slot decoded
         CU_OK(h, cudaMemcpyAsync(h->slot_in[slot], (const char *)images_host + (size_t)b0 * img_elems * esz,
                                  (size_t)nb * img_elems * esz, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
-        mark("h2d", k, h->copy_stream);
         CU_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
         FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr};
         rc = forward_impl(h, io, nb, mode, s);
         if (rc != LWOP_OK) return rc;
         CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
-        mark("fwd", k, s);
         CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
-        lwop_decode_tables t = h->own_tables;
+        lwop_decode_tables t = ln.tables;
         t.counts += (size_t)b0 * LWOP_COUNTS;
         t.joints += (size_t)b0 * LWOP_MAX_JOINTS * 6;
         t.limbs += (size_t)b0 * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 5;
@@ -1018,29 +1084,65 @@ int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batc
             CU_OK(h, cudaMemcpyAsync(paf_host + (size_t)b0 * px * LWOP_NUM_PAFS, h->slot_paf[slot],
                                      (size_t)nb * px * LWOP_NUM_PAFS * 4, cudaMemcpyDeviceToHost, ds));
         CU_OK(h, cudaEventRecord(h->ev_done[slot], ds));
-        mark("dec", k, ds);
     }
-    CU_OK(h, cudaEventRecord(h->ev_join, ds));
-    CU_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-    if (trace) {
-        rc = lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
-        mark("end", 0, s);
-        cudaStreamSynchronize(s);
-        for (size_t i = 1; i < tev.size(); ++i) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, tev[0], tev[i]);
-            fprintf(stderr, "lwop trace: %-8s %8.3f ms\n", tname[i].c_str(), ms);
-        }
-        for (auto e : tev) cudaEventDestroy(e);
-        return rc;
+    // compaction + download of the result tables, still asynchronous: the packed buffers are copied at the
+    // capacities the caller provided (rows beyond a capacity are dropped and reported by lwop_infer_host_end)
+    CU_OK(h, launch_decode_pack(ln.tables, batch, ln.pack_offsets, ln.pk_joints, ln.pk_limbs, ln.pk_persons,
+                                ln.pk_keypoints, ds, &h->launches, (long long)o->joints_cap, (long long)o->limbs_cap,
+                                (long long)o->persons_cap));
+    CU_OK(h, cudaMemcpyAsync(o->counts, ln.tables.counts, (size_t)batch * LWOP_COUNTS * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, ds));
+    if (o->joints_cap) CU_OK(h, cudaMemcpyAsync(o->joints, ln.pk_joints, o->joints_cap * 6 * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (o->limbs_cap) CU_OK(h, cudaMemcpyAsync(o->limbs, ln.pk_limbs, o->limbs_cap * 5 * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (o->persons_cap) {
+        CU_OK(h, cudaMemcpyAsync(o->persons, ln.pk_persons, o->persons_cap * 16 * sizeof(double), cudaMemcpyDeviceToHost, ds));
+        CU_OK(h, cudaMemcpyAsync(o->keypoints, ln.pk_keypoints, o->persons_cap * 42 * sizeof(float), cudaMemcpyDeviceToHost, ds));
     }
-    return lwop_decode_fetch(h, &h->own_tables, batch, o, stream);
+    CU_OK(h, cudaEventRecord(ln.ev_ready, ds));
+    CU_OK(h, cudaStreamWaitEvent(s, ln.ev_ready, 0));       // the caller's stream observes completion as well
+    ln.busy = true;
+    ln.batch = batch;
+    ln.out = *o;
+    *ticket = lane;
+    return LWOP_OK;
+}
+}  // namespace
+
+int lwop_infer_host_end(lwop_handle *h, int ticket) {
+    if (!h || ticket < 0 || ticket >= LWOP_MAX_INFLIGHT || !h->lanes[ticket].busy)
+        return fail(h, LWOP_ERR_INVALID, "bad ticket");
+    lwop_handle::HostLane &ln = h->lanes[ticket];
+    CU_OK(h, cudaSetDevice(h->device));
+    cudaError_t e = cudaEventSynchronize(ln.ev_ready);
+    ln.busy = false;
+    if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("infer_host: ") + cudaGetErrorString(e));
+    size_t nj = 0, np = 0, nc = 0;
+    bool overflow = false;
+    for (int b = 0; b < ln.batch; ++b) {
+        const int32_t *c = ln.out.counts + (size_t)b * LWOP_COUNTS;
+        nj += c[0]; np += c[1]; nc += c[3];
+        overflow |= c[2] != 0;
+    }
+    if (nj > ln.out.joints_cap || nc > ln.out.limbs_cap || np > ln.out.persons_cap)
+        return fail(h, LWOP_ERR_OVERFLOW, "host result buffers too small: need " + std::to_string(nj) + " joint, " +
+                                              std::to_string(nc) + " limb, " + std::to_string(np) + " person rows");
+    if (overflow) return fail(h, LWOP_ERR_OVERFLOW, "a per-image decode table capacity was exceeded (counts[b][2])");
+    return LWOP_OK;
+}
+
+int lwop_infer_host(lwop_handle *h, const void *images_host, int is_u8, int batch, int mode, float thre1,
+                    double thre2, const lwop_packed_tables *o, float *heat_host, float *paf_host, void *stream) {
+    int ticket = -1;
+    int rc = infer_host_begin_impl(h, images_host, is_u8, batch, mode, thre1, thre2, o, heat_host, paf_host, stream,
+                                   &ticket, true);
+    if (rc != LWOP_OK) return rc;
+    return lwop_infer_host_end(h, ticket);
 }
 
 int lwop_set_option(lwop_handle *h, const char *name, long long value) {
     if (!h || !name) return fail(h, LWOP_ERR_INVALID, "null argument");
     if (strcmp(name, "chunk") == 0) {
-        if (value < 1) return fail(h, LWOP_ERR_INVALID, "chunk must be >= 1");
+        if (value < 0) return fail(h, LWOP_ERR_INVALID, "chunk must be >= 0 (0 = library default)");
         h->chunk = (int)value;
         return LWOP_OK;
     }

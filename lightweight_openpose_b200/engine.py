@@ -121,6 +121,9 @@ class Engine:
         self._tables = None
         self._host = None
         self._out = {}
+        self._async_tables = []
+        self._inflight = {}
+        self.last_d2h_bytes = 0
 
     def close(self) -> None:
         if getattr(self, "handle", None):
@@ -212,19 +215,24 @@ class Engine:
             self._tables = (t, s)
         return self._tables
 
-    def _host_tables(self, batch: int):
-        """Pinned host result buffers, grown on demand."""
+    def _new_host_tables(self, batch: int, scale: int = 1):
+        """Pinned host result buffers.  The asynchronous path downloads them at full capacity, so the defaults are
+        sized for typical frames (<= 128 joints / connections, 16 persons per frame) and grown on overflow."""
         torch = _torch()
-        need_j, need_l, need_p = batch * 256, batch * 256, batch * 32
+        nj, nl, npers = batch * 128 * scale, batch * 128 * scale, batch * 16 * scale
+        return {
+            "batch": batch,
+            "counts": torch.zeros((batch, _lib.COUNTS), dtype=torch.int32).pin_memory(),
+            "joints": torch.empty((nj, 6), dtype=torch.float64).pin_memory(),
+            "limbs": torch.empty((nl, 5), dtype=torch.float64).pin_memory(),
+            "persons": torch.empty((npers, 16), dtype=torch.float64).pin_memory(),
+            "keypoints": torch.empty((npers, 42), dtype=torch.float32).pin_memory(),
+        }
+
+    def _host_tables(self, batch: int):
+        """Pinned host result buffers of the synchronous calls, grown on demand."""
         if self._host is None or self._host["batch"] < batch:
-            self._host = {
-                "batch": batch,
-                "counts": torch.zeros((batch, _lib.COUNTS), dtype=torch.int32).pin_memory(),
-                "joints": torch.empty((need_j, 6), dtype=torch.float64).pin_memory(),
-                "limbs": torch.empty((need_l, 5), dtype=torch.float64).pin_memory(),
-                "persons": torch.empty((need_p, 16), dtype=torch.float64).pin_memory(),
-                "keypoints": torch.empty((need_p, 42), dtype=torch.float32).pin_memory(),
-            }
+            self._host = self._new_host_tables(batch)
         return self._host
 
     def _packed_struct(self, hst) -> _lib.PackedTables:
@@ -232,8 +240,13 @@ class Engine:
                                  hst["persons"].data_ptr(), hst["keypoints"].data_ptr(),
                                  hst["joints"].shape[0], hst["limbs"].shape[0], hst["persons"].shape[0])
 
+    @staticmethod
+    def _table_bytes(hst, batch: int) -> int:
+        return int(batch * _lib.COUNTS * 4 + hst["joints"].numel() * 8 + hst["limbs"].numel() * 8
+                   + hst["persons"].numel() * 8 + hst["keypoints"].numel() * 4)
+
     def _grow_host(self, hst, msg: str) -> bool:
-        """Overflow of the *host* buffers: double them and let the caller retry."""
+        """Overflow of the *host* buffers: quadruple them and let the caller retry."""
         if "host result buffers too small" not in msg:
             return False
         torch = _torch()
@@ -321,7 +334,7 @@ class Engine:
     def infer_host(self, images_host, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0,
                    want_maps: bool = False):
         """images_host: pinned (or pageable) CPU tensor / ndarray [B,H,W,3] float32 or uint8.
-        One C call: H2D, forward, decode, D2H.  Returns a list of DecodeResult
+        One C call: H2D, forward, decode, D2H.  Returns a :class:`BatchResult`
         (and the host maps when ``want_maps``)."""
         torch = _torch()
         if isinstance(images_host, np.ndarray):
@@ -345,11 +358,51 @@ class Engine:
                     continue
             _lib.check(rc, self.handle)
             break
+        self.last_d2h_bytes = self._table_bytes(hst, B)
         res = _split_packed(B, hst["counts"].numpy(), hst["joints"].numpy(), hst["limbs"].numpy(),
                             hst["persons"].numpy(), hst["keypoints"].numpy())
         if want_maps:
             return res, heat_h.numpy(), paf_h.numpy()
         return res
+
+    def infer_host_begin(self, images_host, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0) -> int:
+        """Asynchronous form: enqueues upload, forward, decode and the download of the result tables for this
+        batch and returns a ticket at once; :meth:`infer_host_end` waits for it.  Keeping two batches in flight
+        (begin k+1 before end k) overlaps the upload of one with the kernels of the other.  ``images_host``
+        must be pinned and stay alive until the matching ``infer_host_end``."""
+        torch = _torch()
+        if isinstance(images_host, np.ndarray):
+            images_host = torch.from_numpy(np.ascontiguousarray(images_host))
+        B = images_host.shape[0]
+        is_u8 = images_host.dtype == torch.uint8
+        free = [t for t in self._async_tables if t["batch"] >= B and not t.get("busy")]
+        hst = free[0] if free else self._new_host_tables(B)
+        if not free:
+            self._async_tables.append(hst)
+        p = self._packed_struct(hst)
+        ticket = C.c_int(-1)
+        rc = self.lib.lwop_infer_host_begin(self.handle, images_host.data_ptr(), int(is_u8), B, _MODES[mode],
+                                            float(np.float32(thre1)), float(thre2), C.byref(p), None, None,
+                                            self._stream(), C.byref(ticket))
+        _lib.check(rc, self.handle)
+        hst["busy"] = True
+        self._inflight[ticket.value] = (B, hst, images_host, mode, thre1, thre2)
+        return ticket.value
+
+    def infer_host_end(self, ticket: int) -> "BatchResult":
+        B, hst, images_host, mode, thre1, thre2 = self._inflight.pop(ticket)
+        rc = self.lib.lwop_infer_host_end(self.handle, ticket)
+        hst["busy"] = False
+        if rc == _lib.ERR_OVERFLOW:
+            msg = self.lib.lwop_last_error(self.handle).decode()
+            if self._grow_host(hst, msg):
+                # this batch needs larger result buffers: run it again synchronously with the grown ones
+                self._host = hst
+                return self.infer_host(images_host, mode, thre1, thre2)
+        _lib.check(rc, self.handle)
+        self.last_d2h_bytes = self._table_bytes(hst, B)
+        return _split_packed(B, hst["counts"].numpy(), hst["joints"].numpy(), hst["limbs"].numpy(),
+                             hst["persons"].numpy(), hst["keypoints"].numpy())
 
     def step_descs(self):
         """[(layer, is_depthwise, in_h, in_w, cin, cout, ksize, stride, dilation, kernel), ...] with kernel
