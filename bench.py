@@ -166,10 +166,13 @@ def run_reference(args, rank: int, world: int):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
-def classify_step(desc):
+def classify_step(desc, next_desc=None):
+    """Kernel class of a step = the CUDA kernel (template family) that runs it."""
     layer, is_dw, h, w, cin, cout, k, stride, dil, tc = desc
     if tc == 2:
-        return "sep_fused_dw3x3_pw1x1"
+        # sep_conv_kernel<..., NH=2>: Cout = 512 in one pass over all 512 TMEM columns (layers 6-11, tensor/L2-bound);
+        # NH=1 instantiations: the narrower separable layers (HBM-bound)
+        return "sep_fused_cout512" if next_desc is not None and next_desc[5] == 512 else "sep_fused_cout64_256"
     if tc == 4:
         return "head_pair_fused_1x1_1x1"
     if tc == 3:
@@ -328,7 +331,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         acc /= n_prof
         classes = {}
         for i, (d, ms) in enumerate(zip(descs, acc)):
-            cls = classify_step(d)
+            cls = classify_step(d, descs[i + 1] if i + 1 < len(descs) else None)
             if cls is None:
                 continue
             c = classes.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
@@ -361,6 +364,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             achieved = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                tr = json.load(fh)
+            if tr.get("batch") == batch and dom in tr["traffic_bytes_per_launch"]:
+                roof["traffic"] = tr["traffic_bytes_per_launch"][dom]
+                roof["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, one launch)"
+                roof["algorithmic_bytes_per_launch"] = dc["bytes"] / dc["launches"]
+        except (OSError, ValueError, KeyError):
+            pass
         roof["kernel"] = dom
         roof["launches_per_step"] = dc["launches"]
         roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
@@ -374,7 +387,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if args.dump_steps:
             with open(args.dump_steps, "w") as fh:
                 for i, (d, ms) in enumerate(zip(descs, acc)):
-                    if classify_step(d) is None:
+                    kind = classify_step(d, descs[i + 1] if i + 1 < len(descs) else None)
+                    if kind is None:
                         continue
                     fl, by = step_work(d, batch)
                     if d[9] == 2:
@@ -383,7 +397,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     if d[9] == 4:
                         fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
                         by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
-                    fh.write(json.dumps({"layer": d[0], "kind": classify_step(d), "in_hw": [d[2], d[3]], "cin": d[4],
+                    fh.write(json.dumps({"layer": d[0], "kind": kind, "in_hw": [d[2], d[3]], "cin": d[4],
                                          "cout": descs[i + 1][5] if d[9] == 2 else d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
                                          "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
                                          "gbs": round(by / (ms * 1e-3) / 1e9, 1)}) + "\n")
