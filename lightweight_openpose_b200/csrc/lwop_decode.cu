@@ -10,6 +10,8 @@
 // intrinsics so the compiler cannot contract it into FMAs: the sequence of
 // roundings is the one of the numpy/cv2 code (float32 two-pass bicubic,
 // float64 limb scores).
+#include <stdlib.h>
+
 #include "lwop_kernels.cuh"
 
 namespace lwop {
@@ -76,7 +78,7 @@ __device__ __forceinline__ int cv_round(double v) { return (int)rint(v); }
 // ---------------------------------------------------------------------------
 // K1: per (image, joint channel): threshold, greedy radius-5 NMS, refinement.
 // ---------------------------------------------------------------------------
-constexpr int kRefineMax = 64;      // separable refinement handles up-sampled patches up to 64 x 64
+constexpr int kRefineMax = 48;      // separable refinement handles up-sampled patches up to 48 x 48 (5 x 8 = 40 here)
 
 __global__ void __launch_bounds__(256)
 peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor, int mode,
@@ -85,9 +87,7 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
     const int npix = h * w;
     float *val = reinterpret_cast<float *>(smem_raw);                 // the channel's map
     int *cand = reinterpret_cast<int *>(val + npix);                  // candidate pixels; index < 0 = suppressed
-    __shared__ int s_nc, s_best_p, s_n;
-    __shared__ float s_wv[8];
-    __shared__ int s_wp[8];
+    __shared__ int s_nc, s_n;
     __shared__ int s_kept[LWOP_MAX_PEAKS];
     // per-warp scratch of the separable refinement: horizontal pass + tap tables
     __shared__ float s_h[8][5][kRefineMax];
@@ -98,18 +98,27 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const float *src = heat + (long long)b * npix * C + ch;
     if (tid == 0) { s_nc = 0; s_n = 0; }
-    __syncthreads();
-    for (int p = tid; p < npix; p += blockDim.x) {
-        const float v = src[(long long)p * C];
-        val[p] = v;
-        if (v > thre1) cand[atomicAdd(&s_nc, 1)] = p;               // np.where(img > thre1), pose_decode.py:54
+    // channel plane -> shared memory: the strided loads are issued in independent batches of 8 per thread so
+    // their latencies overlap (the candidate scan runs afterwards on the shared-memory copy)
+    for (int p0 = 0; p0 < npix; p0 += 8 * (int)blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int p = p0 + k * (int)blockDim.x + tid;
+            v[k] = p < npix ? __ldg(src + (long long)p * C) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int p = p0 + k * (int)blockDim.x + tid;
+            if (p < npix) val[p] = v[k];
+        }
     }
+    __syncthreads();
+    for (int p = tid; p < npix; p += blockDim.x)
+        if (val[p] > thre1) cand[atomicAdd(&s_nc, 1)] = p;          // np.where(img > thre1), pose_decode.py:54
     __syncthreads();
     const int nc = s_nc;
 
-    // The greedy loop of find_peaks_v2 (:62-70) verbatim: take the best remaining candidate, drop every
-    // remaining candidate within Euclidean distance 5 of it, repeat.  "Best" = larger score, exact ties
-    // towards the larger row-major index.  One block-wide arg-max per kept peak.
     int n = 0;
     if (mode & LWOP_PEAKS_CROSS) {
         // find_peaks (:37-49): value > thre1 and equal to the maximum over the 3x3 cross footprint (scipy
@@ -150,49 +159,58 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
             n = LWOP_MAX_PEAKS;
         }
         __syncthreads();
-    } else
-    while (true) {
-        float bv = -INFINITY;
-        int bp = -1;
-        for (int i = tid; i < nc; i += blockDim.x) {
-            const int p = cand[i];
-            if (p < 0) continue;
-            const float v = val[p];
-            if (v > bv || (v == bv && p > bp)) { bv = v; bp = p; }
-        }
+    } else {
+        // The greedy loop of find_peaks_v2 (:62-70) verbatim: take the best remaining candidate, drop every
+        // remaining candidate within Euclidean distance 5 of it, repeat.  "Best" = larger score, exact ties
+        // towards the larger row-major index.
+        // One block-wide arg-max per kept peak (a single-warp variant was measured slower: the frames' heavy
+        // channels have ~1000 candidates and 30-40 peaks, and they set the kernel's tail).
+        __shared__ float s_wv[8];
+        __shared__ int s_wp[8];
+        __shared__ int s_best_p;
+        while (true) {
+            float bv = -INFINITY;
+            int bp = -1;
+            for (int i = tid; i < nc; i += blockDim.x) {
+                const int p = cand[i];
+                if (p < 0) continue;
+                const float v = val[p];
+                if (v > bv || (v == bv && p > bp)) { bv = v; bp = p; }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-            if (ov > bv || (ov == bv && op > bp)) { bv = ov; bp = op; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (ov > bv || (ov == bv && op > bp)) { bv = ov; bp = op; }
+            }
+            if (lane == 0) { s_wv[warp] = bv; s_wp[warp] = bp; }
+            __syncthreads();
+            if (tid == 0) {
+                float fv = s_wv[0];
+                int fp = s_wp[0];
+                for (int k = 1; k < nwarps; ++k)
+                    if (s_wv[k] > fv || (s_wv[k] == fv && s_wp[k] > fp)) { fv = s_wv[k]; fp = s_wp[k]; }
+                s_best_p = fp;
+                if (fp >= 0 && n < LWOP_MAX_PEAKS) s_kept[n] = fp;
+            }
+            __syncthreads();
+            const int best = s_best_p;
+            if (best < 0) break;
+            if (n >= LWOP_MAX_PEAKS) {                                    // more peaks than the table holds
+                if (tid == 0) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
+                break;
+            }
+            ++n;
+            const int by = best / w, bx = best - by * w;
+            for (int i = tid; i < nc; i += blockDim.x) {
+                const int p = cand[i];
+                if (p < 0) continue;
+                const int py = p / w, px = p - py * w;
+                const int dy = py - by, dx = px - bx;
+                if (dx * dx + dy * dy <= kRadius * kRadius) cand[i] = -1;   // keeps dis > dis_thres (:68); drops `best` too
+            }
+            __syncthreads();
         }
-        if (lane == 0) { s_wv[warp] = bv; s_wp[warp] = bp; }
-        __syncthreads();
-        if (tid == 0) {
-            float fv = s_wv[0];
-            int fp = s_wp[0];
-            for (int k = 1; k < nwarps; ++k)
-                if (s_wv[k] > fv || (s_wv[k] == fv && s_wp[k] > fp)) { fv = s_wv[k]; fp = s_wp[k]; }
-            s_best_p = fp;
-            if (fp >= 0 && n < LWOP_MAX_PEAKS) s_kept[n] = fp;
-        }
-        __syncthreads();
-        const int best = s_best_p;
-        if (best < 0) break;
-        if (n >= LWOP_MAX_PEAKS) {                                    // more peaks than the table holds
-            if (tid == 0) atomicOr(&counts[b * LWOP_COUNTS + 2], 1);
-            break;
-        }
-        ++n;
-        const int by = best / w, bx = best - by * w;
-        for (int i = tid; i < nc; i += blockDim.x) {
-            const int p = cand[i];
-            if (p < 0) continue;
-            const int py = p / w, px = p - py * w;
-            const int dy = py - by, dx = px - bx;
-            if (dx * dx + dy * dy <= kRadius * kRadius) cand[i] = -1;   // keeps dis > dis_thres (:68); drops `best` too
-        }
-        __syncthreads();
     }
     if (tid == 0) peak_counts[b * 16 + ch] = n;
 
@@ -335,28 +353,35 @@ __device__ __forceinline__ AxisTaps axis_taps(int d, double scale, int n) {
 }
 
 // ---------------------------------------------------------------------------
-// K2: per (image, limb type): score every (src, dst) joint pair, keep per src
-// the best dst.  One warp per src joint, lanes over dst joints.
+// K2: per (image, limb type): score every (src, dst) joint pair, keep per src the best dst.
+// Work is spread over (pair, sample) items -- one thread evaluates ONE of the 10 line-integral samples of one pair
+// (the 16-tap bicubic of both PAF channels) -- so the long dependent chains of global loads run in parallel; the
+// per-pair reduction and the per-source arg-max then replay the reference's sequential order exactly.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kPairChunk = 192;     // (src, dst) pairs scored per pass
+constexpr int kLimbThreads = 256;
+
+__global__ void __launch_bounds__(kLimbThreads)
 limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double thre2, int direct,
              const float *__restrict__ peaks, const int *__restrict__ peak_counts, double *__restrict__ limbs,
              int *__restrict__ counts) {
-    const int t = blockIdx.x, b = blockIdx.y;
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int ja = c_limb_src[t], jb = c_limb_dst[t];
     const int *pc = peak_counts + b * 16;
     const int na = pc[ja], nb = pc[jb];
-    __shared__ int s_rows;
-    __shared__ unsigned char s_has[LWOP_MAX_PEAKS];
-    __shared__ double s_score[LWOP_MAX_PEAKS];
-    __shared__ int s_j[LWOP_MAX_PEAKS];
-    if (threadIdx.x == 0) s_rows = 0;
-    for (int i = threadIdx.x; i < LWOP_MAX_PEAKS; i += blockDim.x) s_has[i] = 0;
-    __syncthreads();
+    __shared__ double s_val[kPairChunk][kSamples];
+    __shared__ double s_mean[kPairChunk];
+    __shared__ unsigned char s_ok[kPairChunk];
+    __shared__ double s_best[LWOP_MAX_PEAKS];
+    __shared__ int s_bestj[LWOP_MAX_PEAKS];
     double *out = limbs + ((long long)b * LWOP_NUM_LIMBS + t) * LWOP_MAX_PEAKS * 5;
     if (na == 0 || nb == 0) {                                     // (:224-228)
-        if (threadIdx.x == 0) counts[b * LWOP_COUNTS + 18 + t] = 0;
+        if (tid == 0) counts[b * LWOP_COUNTS + 18 + t] = 0;
         return;
+    }
+    for (int i = tid; i < na; i += kLimbThreads) {
+        s_best[i] = 0.0;                                          // best_score = 0.0 (:243)
+        s_bestj[i] = 0x7fffffff;
     }
     int ida = 0, idb = 0;                                         // unique ids count channels then peaks (:135,183)
     for (int c = 0; c < ja; ++c) ida += pc[c];
@@ -364,37 +389,35 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
     const float *pa = peaks + ((long long)b * LWOP_NUM_JOINTS + ja) * LWOP_MAX_PEAKS * 4;
     const float *pb = peaks + ((long long)b * LWOP_NUM_JOINTS + jb) * LWOP_MAX_PEAKS * 4;
     const float *pafb = paf + (long long)b * (direct ? (long long)H * W : (long long)h * w) * LWOP_NUM_PAFS;
-    const int cx_ch = 2 * t, cy_ch = 2 * t + 1;                   // paf_xy_coords_per_limb (:23-24)
+    const int cx_ch = 2 * t;                                      // paf_xy_coords_per_limb (:23-24): (2t, 2t+1)
     const double scale_x = 1.0 / ((double)W / (double)w);         // cv2: 1. / (dsize / ssize)
     const double scale_y = 1.0 / ((double)H / (double)h);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int total = na * nb;
+    __syncthreads();
 
-    for (int i = warp; i < na; i += nwarps) {
-        const double ax = pa[i * 4 + 0], ay = pa[i * 4 + 1];
-        double best = 0.0;                                        // best_score = 0.0 (:243)
-        int best_j = 0x7fffffff;
-        for (int j = lane; j < nb; j += 32) {
+    for (int chunk0 = 0; chunk0 < total; chunk0 += kPairChunk) {
+        const int npairs = min(kPairChunk, total - chunk0);
+        // ---- one thread per (pair, sample): score_k = paf(x_k, y_k) . unit(limb) ----
+        for (int item = tid; item < npairs * kSamples; item += kLimbThreads) {
+            const int pi = item / kSamples, k = item - pi * kSamples;
+            const int gp = chunk0 + pi;
+            const int i = gp / nb, j = gp - i * nb;
+            const double ax = pa[i * 4 + 0], ay = pa[i * 4 + 1];
             const double bx = pb[j * 4 + 0], by = pb[j * 4 + 1];
             const double dx = bx - ax, dy = by - ay;              // limb_dir (:249)
-            if (fabs(dx) > (double)W || fabs(dy) > (double)H) continue;   // (:209,250)
             const double norm = __dadd_rn(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), 1e-8);   // (:255)
             const double ux = dx / norm, uy = dy / norm;
             const double stepx = dx / 9.0, stepy = dy / 9.0;      // np.linspace(start, stop, 10)
-            double s[kSamples];
-            int above = 0;
-#pragma unroll
-            for (int k = 0; k < kSamples; ++k) {
-                double fxk = k == kSamples - 1 ? bx : __dadd_rn(__dmul_rn((double)k, stepx), ax);
-                double fyk = k == kSamples - 1 ? by : __dadd_rn(__dmul_rn((double)k, stepy), ay);
-                int X = (int)rint(fxk), Y = (int)rint(fyk);       // np.round: half to even (:260-264)
-                X = clampi(X, 0, W - 1);                          // joints are inside the frame; guard only
-                Y = clampi(Y, 0, H - 1);
-                if (direct) {       // caller passed the up-sampled PAF (find_connected_joints stage API, :267-268)
-                    const float2 v = *reinterpret_cast<const float2 *>(pafb + ((long long)Y * W + X) * LWOP_NUM_PAFS + cx_ch);
-                    s[k] = __dadd_rn(__dmul_rn((double)v.x, ux), __dmul_rn((double)v.y, uy));
-                    above += s[k] > thre2 ? 1 : 0;
-                    continue;
-                }
+            const double fxk = k == kSamples - 1 ? bx : __dadd_rn(__dmul_rn((double)k, stepx), ax);
+            const double fyk = k == kSamples - 1 ? by : __dadd_rn(__dmul_rn((double)k, stepy), ay);
+            int X = (int)rint(fxk), Y = (int)rint(fyk);           // np.round: half to even (:260-264)
+            X = clampi(X, 0, W - 1);                              // joints are inside the frame; guard only
+            Y = clampi(Y, 0, H - 1);
+            double sk;
+            if (direct) {       // caller passed the up-sampled PAF (find_connected_joints stage API, :267-268)
+                const float2 v = *reinterpret_cast<const float2 *>(pafb + ((long long)Y * W + X) * LWOP_NUM_PAFS + cx_ch);
+                sk = __dadd_rn(__dmul_rn((double)v.x, ux), __dmul_rn((double)v.y, uy));
+            } else {
                 const AxisTaps tx = axis_taps(X, scale_x, w), ty = axis_taps(Y, scale_y, h);
                 float rx[4], ry[4];
 #pragma unroll
@@ -411,42 +434,59 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
                     ry[r] = dot4(vy, tx.c);
                 }
                 const double px = (double)dot4_rev(rx, ty.c), py = (double)dot4_rev(ry, ty.c);
-                s[k] = __dadd_rn(__dmul_rn(px, ux), __dmul_rn(py, uy));   // intermed_paf.dot(limb_dir) (:270)
-                above += s[k] > thre2 ? 1 : 0;
+                sk = __dadd_rn(__dmul_rn(px, ux), __dmul_rn(py, uy));   // intermed_paf.dot(limb_dir) (:270)
             }
-            // numpy pairwise mean of 10 float64 values (:271)
-            double sum = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
-                                   __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-            sum = __dadd_rn(__dadd_rn(sum, s[8]), s[9]);
-            const double mean = sum / 10.0;
-            if (above > 8 && mean > thre2 && mean > best) {       // criteria (:276-285); first j wins ties
-                best = mean;
-                best_j = j;
-            }
+            s_val[pi][k] = sk;
         }
+        __syncthreads();
+        // ---- one thread per pair: the acceptance criteria (:271-283) ----
+        for (int pi = tid; pi < npairs; pi += kLimbThreads) {
+            const int gp = chunk0 + pi;
+            const int i = gp / nb, j = gp - i * nb;
+            const double dx = (double)pb[j * 4 + 0] - (double)pa[i * 4 + 0], dy = (double)pb[j * 4 + 1] - (double)pa[i * 4 + 1];
+            const double *sv = s_val[pi];
+            int above = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-            if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+            for (int k = 0; k < kSamples; ++k) above += sv[k] > thre2 ? 1 : 0;
+            // numpy pairwise mean of 10 float64 values (:271)
+            double sum = __dadd_rn(__dadd_rn(__dadd_rn(sv[0], sv[1]), __dadd_rn(sv[2], sv[3])),
+                                   __dadd_rn(__dadd_rn(sv[4], sv[5]), __dadd_rn(sv[6], sv[7])));
+            sum = __dadd_rn(__dadd_rn(sum, sv[8]), sv[9]);
+            const double mean = sum / 10.0;
+            const bool skip = fabs(dx) > (double)W || fabs(dy) > (double)H;       // (:209,250)
+            s_mean[pi] = mean;
+            s_ok[pi] = (!skip && above > 8 && mean > thre2) ? 1 : 0;
         }
-        if (lane == 0 && best_j != 0x7fffffff) {
-            s_has[i] = 1;
-            s_score[i] = best;
-            s_j[i] = best_j;
+        __syncthreads();
+        // ---- one thread per source joint: best destination so far, j ascending, strict > (first j wins ties, :285) ----
+        const int i0 = chunk0 / nb, i1 = (chunk0 + npairs - 1) / nb;
+        for (int i = i0 + tid; i <= i1; i += kLimbThreads) {
+            const int jlo = i == i0 ? chunk0 - i0 * nb : 0;
+            const int jhi = i == i1 ? (chunk0 + npairs - 1) - i1 * nb : nb - 1;
+            double best = s_best[i];
+            int best_j = s_bestj[i];
+            for (int j = jlo; j <= jhi; ++j) {
+                const int pi = i * nb + j - chunk0;
+                if (s_ok[pi] && s_mean[pi] > best) {
+                    best = s_mean[pi];
+                    best_j = j;
+                }
+            }
+            s_best[i] = best;
+            s_bestj[i] = best_j;
         }
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {                                       // rows in src order (:297)
+    if (tid == 0) {                                               // rows in src order (:297)
         int r = 0;
         for (int i = 0; i < na; ++i)
-            if (s_has[i]) {
+            if (s_bestj[i] != 0x7fffffff) {
                 double *o = out + r * 5;
                 o[0] = (double)(ida + i);
-                o[1] = (double)(idb + s_j[i]);
-                o[2] = s_score[i];
+                o[1] = (double)(idb + s_bestj[i]);
+                o[2] = s_best[i];
                 o[3] = (double)i;
-                o[4] = (double)s_j[i];
+                o[4] = (double)s_bestj[i];
                 ++r;
             }
         counts[b * LWOP_COUNTS + 18 + t] = r;
@@ -468,6 +508,8 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     __shared__ float s_score[LWOP_MAX_JOINTS];           // joint scores (float32 values, exact in float)
     __shared__ double s_conn[LWOP_MAX_PEAKS][3];         // (src_id, dst_id, score) of the current limb type
     __shared__ int s_off[LWOP_NUM_JOINTS + 1];
+    __shared__ float s_x[LWOP_MAX_JOINTS], s_y[LWOP_MAX_JOINTS];   // joint coordinates for the keypoint table
+    __shared__ unsigned char s_type[LWOP_MAX_JOINTS];
     double *Pg = work + (long long)b * kMaxWorkPersons * 16;
     auto P = [&](int k) -> double * { return k < kSmemPersons ? Ps[k] : Pg + (long long)(k - kSmemPersons) * 16; };
 
@@ -497,6 +539,9 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
             o[4] = 0.0;
             o[5] = (double)c;
             s_score[id] = pk[i * 4 + 2];
+            s_x[id] = pk[i * 4 + 0];
+            s_y[id] = pk[i * 4 + 1];
+            s_type[id] = (unsigned char)c;
         }
     }
     __syncwarp();
@@ -548,13 +593,11 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                     if (lane == 14) p0[14] = __dadd_rn(__dadd_rn(p0[14], p1[14]), s);
                     if (lane == 15) p0[15] += p1[15];
                     __syncwarp();
-                    __threadfence_block();
                     for (int k = m1; k + 1 < np; ++k) {           // list.pop(m1)
                         double v = 0.0;
                         if (lane < 16) v = P(k + 1)[lane];
                         if (lane < 16) P(k)[lane] = v;
                         __syncwarp();
-                        __threadfence_block();
                     }
                     --np;
                 } else if (lane == 0) {
@@ -577,7 +620,6 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                 }
             }
             __syncwarp();
-            __threadfence_block();
         }
     }
     // drop persons with < 3 parts or mean score < 0.2 (:382-391); keypoint table (:403-429)
@@ -601,10 +643,10 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
                 if (ia < 0.0 || ib < 0.0) continue;               // `-1 in joint_indices` (:411)
                 const double ids[2] = {ia, ib};
                 for (int e = 0; e < 2; ++e) {
-                    const double *jrow = jl + (long long)(int)ids[e] * 6;
-                    const int jt = (int)jrow[5];
-                    ko[kept * 42 + jt * 3 + 0] = (float)jrow[0];
-                    ko[kept * 42 + jt * 3 + 1] = (float)jrow[1];
+                    const int jid = (int)ids[e];
+                    const int jt = s_type[jid];
+                    ko[kept * 42 + jt * 3 + 0] = s_x[jid];
+                    ko[kept * 42 + jt * 3 + 1] = s_y[jid];
                     ko[kept * 42 + jt * 3 + 2] = 1.0f;
                 }
             }
@@ -726,7 +768,7 @@ cudaError_t launch_decode(const DecodeArgs &a, cudaStream_t s, long long *launch
     const double factor = (double)a.H / (double)a.h;              // scale = img_H / heat_H (:462)
     peaks_kernel<<<dim3(LWOP_NUM_JOINTS, a.B), 256, smem, s>>>(a.heat, a.h, a.w, LWOP_NUM_JOINTS, a.thre1, factor, 0,
                                                                a.peaks, a.peak_counts, a.t.counts);
-    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), 128, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, 0, a.peaks,
+    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, a.B), kLimbThreads, 0, s>>>(a.paf, a.h, a.w, a.H, a.W, a.thre2, 0, a.peaks,
                                                            a.peak_counts, a.t.limbs, a.t.counts);
     group_kernel<<<a.B, 32, 0, s>>>(a.peaks, a.peak_counts, a.t.limbs, a.t.counts, a.t.joints, a.t.persons,
                                     a.t.keypoints, a.work);
@@ -754,7 +796,7 @@ cudaError_t launch_decode_peaks(const float *heat, int B, int h, int w, double f
 
 cudaError_t launch_decode_limbs(const float *paf, int upsampled, int B, int h, int w, int H, int W, double thre2,
                                 const float *peaks, const int *peak_counts, double *limbs, int *counts, cudaStream_t s) {
-    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, B), 128, 0, s>>>(paf, h, w, H, W, thre2, upsampled ? 1 : 0, peaks, peak_counts,
+    limbs_kernel<<<dim3(LWOP_NUM_LIMBS, B), kLimbThreads, 0, s>>>(paf, h, w, H, W, thre2, upsampled ? 1 : 0, peaks, peak_counts,
                                                          limbs, counts);
     return cudaGetLastError();
 }

@@ -1099,7 +1099,8 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
         CU_OK(h, cudaMemcpyAsync(o->keypoints, ln.pk_keypoints, o->persons_cap * 42 * sizeof(float), cudaMemcpyDeviceToHost, ds));
     }
     CU_OK(h, cudaEventRecord(ln.ev_ready, ds));
-    CU_OK(h, cudaStreamWaitEvent(s, ln.ev_ready, 0));       // the caller's stream observes completion as well
+    // `s` deliberately does NOT wait for ev_ready: the next batch's forward may start while this batch is still
+    // being decoded / downloaded on the decode stream (lwop_infer_host_end synchronises on ev_ready)
     ln.busy = true;
     ln.batch = batch;
     ln.out = *o;
