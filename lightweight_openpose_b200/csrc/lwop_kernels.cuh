@@ -33,6 +33,10 @@ cudaError_t launch_depthwise_simple(const DwArgs &a, cudaStream_t s);
 cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s);
 cudaError_t set_conv1_constants(const float *w_host_n27, const float *b_host);   // per device, at weight load
 cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s);
+// lwop_conv1.cu -- the first layer as a tcgen05 implicit GEMM (im2col rows assembled by producer warps)
+void conv1_tc_pack_weights(const float *w_n27, uint16_t *w_u8_32x32, uint16_t *w_f32_32x64);
+cudaError_t launch_conv1_tc(const void *in, int in_is_u8, void *out, const void *w_u8_dev, const void *w_f32_dev,
+                            const float *bias_dev, int B, int H, int W, cudaStream_t s);
 cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStream_t s);
 cudaError_t launch_preprocess_bgr(const uint8_t *in, int B, int Hs, int Ws, uint8_t *out, int H, int W, cudaStream_t s);
 cudaError_t launch_pack_bf16(const float *src, void *dst, long long rows, int cols, int cols_padded,

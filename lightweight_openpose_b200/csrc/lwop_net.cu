@@ -116,6 +116,8 @@ struct lwop_handle {
     void *w_bf16[kNumLayers] = {};               // [Cout_pad][taps][Cin_pad] bf16
     float *b_pad[kNumLayers] = {};               // [Cout_pad] fp32
     float *w_f32pad[kNumLayers] = {};            // fp32 weights with padded Cin (only layer 24: 40 -> 64)
+    void *c1_w_u8 = nullptr, *c1_w_f32 = nullptr;   // first layer, tensor-core operand tables (lwop_conv1.cu)
+    float *c1_bias = nullptr;
 
     // program + arenas
     std::vector<Step> steps;
@@ -477,7 +479,14 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
         const void *in = st.in == B_IN ? (const void *)in_f32 : arena[st.in];
         float *out2 = st.out2 == B_H1 ? io.h1 : st.out2 == B_P1 ? io.p1 : nullptr;
         if (st.layer == 0) {
-            if (!f32) {
+            // The tensor-core variant of this layer (lwop_conv1.cu) is correct but measured SLOWER than the fp32-FMA
+            // kernel on B200 (1.05 ms vs 0.39 ms per 256 frames: 128x32x32 MMAs are too small to amortise the
+            // per-tile barrier round trips of a one-CTA-per-SM pipeline); it stays opt-in: LWOP_CONV1_TC=1.
+            static const bool c1_tc = getenv("LWOP_CONV1_TC") != nullptr;
+            if (mode == LWOP_MODE_BF16 && c1_tc) {
+                CU_OK(h, launch_conv1_tc(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, h->c1_w_u8, h->c1_w_f32,
+                                         h->c1_bias, batch, st.H, st.W, s));
+            } else if (!f32) {
                 CU_OK(h, launch_conv1_bf16(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, batch, st.H, st.W, s));
             } else {
                 ConvArgs a{};
@@ -737,6 +746,9 @@ int lwop_destroy(lwop_handle *h) {
         if (h->b_pad[i]) cudaFree(h->b_pad[i]);
         if (h->w_f32pad[i]) cudaFree(h->w_f32pad[i]);
     }
+    if (h->c1_w_u8) cudaFree(h->c1_w_u8);
+    if (h->c1_w_f32) cudaFree(h->c1_w_f32);
+    if (h->c1_bias) cudaFree(h->c1_bias);
     if (h->blob) cudaFree(h->blob);
     if (h->peaks) cudaFree(h->peaks);
     if (h->peak_counts) cudaFree(h->peak_counts);
@@ -805,6 +817,16 @@ int lwop_load_weights(lwop_handle *h, const float *host_blob, size_t num_floats)
     }
     // first conv: taps in constant memory (one process drives one GPU, so the per-device symbol is unambiguous)
     CU_OK(h, set_conv1_constants(host_blob + h->off_w[0], host_blob + h->off_b[0]));
+    {   // the same layer as tensor-core operand tables (default first-layer kernel in bf16 mode)
+        uint16_t w8[32 * 32], wf[32 * 64];
+        conv1_tc_pack_weights(host_blob + h->off_w[0], w8, wf);
+        if (!h->c1_w_u8) CU_OK(h, cudaMalloc(&h->c1_w_u8, sizeof(w8)));
+        if (!h->c1_w_f32) CU_OK(h, cudaMalloc(&h->c1_w_f32, sizeof(wf)));
+        if (!h->c1_bias) CU_OK(h, cudaMalloc(&h->c1_bias, 32 * sizeof(float)));
+        CU_OK(h, cudaMemcpy(h->c1_w_u8, w8, sizeof(w8), cudaMemcpyHostToDevice));
+        CU_OK(h, cudaMemcpy(h->c1_w_f32, wf, sizeof(wf), cudaMemcpyHostToDevice));
+        CU_OK(h, cudaMemcpy(h->c1_bias, host_blob + h->off_b[0], 32 * sizeof(float), cudaMemcpyHostToDevice));
+    }
     // bf16 operand layouts for the tensor-core path: [Cout_pad][taps][Cin_pad], bias [Cout_pad]
     for (int i = 1; i < kNumLayers; ++i) {
         const LayerSpec &l = kLayers[i];

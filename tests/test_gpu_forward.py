@@ -76,7 +76,9 @@ def test_uint8_input_path(variables):
     eng = engine.get_engine(256, 256, 2)
     hu, pu = (t.clone() for t in eng.forward(torch.from_numpy(u8).cuda()))
     hf, pf = eng.forward(torch.from_numpy(xf).cuda())
-    assert torch.equal(hu, hf) and torch.equal(pu, pf)
+    assert torch.equal(hu, hf) and torch.equal(pu, pf)         # `/ 255.` on the device == on the host, bit for bit
+    oh, op = ForwardOracle(variables)(xf)
+    assert _maxabs(hu.cpu().numpy(), oh) <= TOL_BF16 and _maxabs(pu.cpu().numpy(), op) <= TOL_BF16
     hu32 = eng.forward(torch.from_numpy(u8).cuda(), mode="fp32")[0].clone()
     hf32, _ = eng.forward(torch.from_numpy(xf).cuda(), mode="fp32")
     assert torch.equal(hu32, hf32)
@@ -92,3 +94,29 @@ def test_graph_replay_is_deterministic_and_counts_launches(variables):
     torch.cuda.synchronize()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert 30 <= n <= 57    # 57 conv steps; fused separable layers and fused head pairs launch one kernel for 2 / 4 steps
+
+
+def test_async_host_path_matches_synchronous(variables):
+    """lwop_infer_host_begin/_end with two batches in flight: same tables as one blocking lwop_infer_host per batch
+    and as forward + decode on device-resident frames."""
+    eng = engine.Engine(368, 368, max_batch=6, device=0)
+    eng.load_variables(variables, "synthetic")
+    batches = [np.stack([synth.synth_image(100 * k + s, 368, 368) for s in range(n)]) for k, n in enumerate((6, 4, 6, 1))]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    sync = [eng.infer_host(p) for p in pinned]
+    tickets = [eng.infer_host_begin(pinned[0])]
+    got = []
+    for p in pinned[1:]:
+        tickets.append(eng.infer_host_begin(p))
+        got.append(eng.infer_host_end(tickets.pop(0)))
+    got.append(eng.infer_host_end(tickets.pop(0)))
+    for a, b, frames in zip(got, sync, batches):
+        assert len(a) == len(b) == frames.shape[0]
+        for ra, rb in zip(a, b):
+            assert np.array_equal(ra.joint_list, rb.joint_list)
+            assert np.array_equal(ra.person_to_joint_assoc, rb.person_to_joint_assoc)
+            assert np.array_equal(ra.joints, rb.joints)
+        heat, paf = eng.forward(torch.from_numpy(frames).cuda())
+        dev = eng.decode(heat, paf)
+        for ra, rd in zip(a, dev):
+            assert np.array_equal(ra.joint_list, rd.joint_list) and np.array_equal(ra.joints, rd.joints)
