@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "368x368 forward+decode images/sec"
+print_json = print
 H = W = 368
 PARAM = {"thre1": 0.1, "thre2": 0.0}
 
@@ -160,7 +161,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_json(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------
@@ -404,7 +405,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 contract; cheap enough to always run) ----
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is an N = 1 line (contract); skipped under torchrun
             threads = os.cpu_count() or 1
             v, dt = cpu_path_images_per_s(args.cpu_images, threads)
             cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
@@ -443,13 +444,27 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        print_json(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 only) is meant to use all host cores,
+    # so the variable is dropped before torch is imported.  stdout carries exactly ONE JSON line: everything else
+    # that libraries print there (NCCL's version banner) is routed to stderr.
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("MKL_NUM_THREADS", None)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str) -> None:
+        os.write(real_stdout, (line + "\n").encode())
+
+    global print_json
+    print_json = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
