@@ -351,6 +351,240 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the N = 128 convolutions: two CTAs of a cluster (one TPC) work on two
+// adjacent M tiles with ONE tcgen05.mma of M = 256 per K step.  Each CTA stages its own A rows but only HALF of
+// the weight tile (64 of the 128 output channels); the tensor cores of both SMs read both halves.  Per SM this
+// halves the weight traffic L2 -> shared memory and the operand reads of B from shared memory -- the two things
+// that bound the single-CTA kernel (profiles/r1c_ncu_full_summary.txt: shared-memory data pipe 76 %, tensor 62 %).
+// Protocol (as in CUTLASS' sm100 2-SM mainloop): the FULL barriers live in the leader CTA (rank 0) and count the
+// bytes of both CTAs' TMA loads; the leader's MMA thread issues for the pair and commits (multicast) to the EMPTY
+// and TMEM-FULL barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's TMEM-EMPTY barrier.
+// ---------------------------------------------------------------------------
+template <int STAGES, int MT>
+struct SmemLayout2Sm {
+    static constexpr int kAHalfBytes = kBlockM * 128;
+    static constexpr int kABytes = MT * kAHalfBytes;
+    static constexpr int kBBytes = 64 * 128;                     // this CTA's half of the [128 x 64] weight chunk
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kBiasOffset = kBarOffset + 256;
+    static constexpr int kStagingOffset = ((kBiasOffset + 512 * 4 + 1023) / 1024) * 1024;
+    static constexpr int kTotal = kStagingOffset + 8 * 4096;
+    static_assert(kTotal <= 232448, "shared memory budget exceeded");
+};
+
+template <bool IM2COL, int STAGES, int MT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+    using L = SmemLayout2Sm<STAGES, MT>;
+    constexpr int BLOCK_N = 128, KSWZ = 128, BLOCK_K = 64;
+    constexpr int kMmasPerBlock = BLOCK_K / 16;
+    constexpr int kTileM = kBlockM * MT;
+    constexpr int kAccCols = MT * BLOCK_N;
+    constexpr uint32_t kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+    constexpr uint32_t kIdesc = make_idesc_bf16(256, BLOCK_N);        // M = 256 across the pair
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_blocks = p.taps * p.k_blocks_per_tap;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_pair_tiles = (p.num_m_tiles + 1) >> 1;             // two M tiles per work item (N = 128: one N tile)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);              // leader's producer arrival (+ the bytes of both CTAs)
+            mbar_init(&empty_bar[i], 1);             // one multicast commit per use
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);             // multicast commit
+            mbar_init(&tmem_empty[i], 8);            // leader only: 4 epilogue warps of each CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_ptr);
+    for (int i = threadIdx.x; i < p.Cout_pad; i += kNumThreads) bias_s[i] = p.bias[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // the peer's barriers exist before anyone signals them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
+                const int m_tile = pt * 2 + rank;
+                const long long m0 = (long long)m_tile * kTileM;
+                int pn[MT], ph[MT], pw[MT];
+#pragma unroll
+                for (int hm = 0; hm < MT; ++hm) {
+                    pn[hm] = ph[hm] = pw[hm] = 0;
+                    if (IM2COL) {
+                        const long long mh = m0 + hm * kBlockM;
+                        const int hw = p.H * p.W;
+                        pn[hm] = (int)(mh / hw);
+                        const int rem = (int)(mh - (long long)pn[hm] * hw);
+                        ph[hm] = rem / p.W;
+                        pw[hm] = rem - ph[hm] * p.W;
+                    }
+                }
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * L::kStageBytes;
+                    unsigned char *sb = sa + L::kABytes;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    const int tap = kb / p.k_blocks_per_tap;
+                    const int c0 = (kb - tap * p.k_blocks_per_tap) * BLOCK_K;
+#pragma unroll
+                    for (int hm = 0; hm < MT; ++hm) {
+                        if (IM2COL) {
+                            const int r = tap / 3, s = tap - r * 3;
+                            tma_load_im2col_4d_2sm(sa + hm * L::kAHalfBytes, &map_a, &full_bar[stage], c0, pw[hm] - p.dil,
+                                                   ph[hm] - p.dil, pn[hm], (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+                        } else {
+                            tma_load_2d_2sm(sa + hm * L::kAHalfBytes, &map_a, &full_bar[stage], c0, (int)(m0 + hm * kBlockM));
+                        }
+                    }
+                    tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BLOCK_K, rank * 64);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only, for the pair) =====================
+        if (leader) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+                    if (elect_one()) {
+                        const uint64_t db = make_kmajor_desc<KSWZ>(sb);
+#pragma unroll
+                        for (int hm = 0; hm < MT; ++hm) {
+                            const uint64_t da = make_kmajor_desc<KSWZ>(sa + hm * L::kAHalfBytes);
+#pragma unroll
+                            for (int k = 0; k < kMmasPerBlock; ++k)
+                                umma_bf16_ss_2sm(d_tmem + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                                 kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_2sm(&empty_bar[stage], 3);                         // frees the slot in both CTAs
+                        if (kb == k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);   // accumulators of both CTAs complete
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpilogueWarp0) {
+        // ===================== epilogue (both CTAs, own 128-row halves) =====================
+        const int q = (warp - kEpilogueWarp0) & 3;
+        const int grp = (warp - kEpilogueWarp0) >> 2;
+        const int acc = grp;
+        uint32_t acc_phase = 0;
+        unsigned char *stg = smem + L::kStagingOffset + (grp * 4 + q) * 4096;
+        int local_tile = 0;
+        for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs, ++local_tile) {
+            if ((local_tile & 1) != grp) continue;
+            const int m_tile = pt * 2 + rank;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int hm = 0; hm < MT; ++hm) {
+                const long long m = (long long)m_tile * kTileM + hm * kBlockM + q * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + hm * BLOCK_N);
+                const bool row_ok = m < p.M;
+#pragma unroll 1
+                for (int g = 0; g < BLOCK_N / 64; ++g) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64), r0);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + 32), r1);
+                    tmem_ld_wait();
+                    if (g == BLOCK_N / 64 - 1 && hm == MT - 1) {   // drained: hand the stage back to the leader's MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+                    }
+                    if (lane == 0) bulk_wait_read_all();
+                    __syncwarp();
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + g * 64);
+                    const uint4 *rp = (p.residual && row_ok)
+                                          ? reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + g * 64)
+                                          : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v[8];
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = j * 8 + e;
+                            const uint32_t raw = c < 32 ? r0[c] : r1[c - 32];
+                            v[e] = apply_act_fast(__uint_as_float(raw) + bb[e], p.act);
+                        }
+                        if (rp) {
+                            const uint4 rr = rp[j];
+                            v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                            v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_out, stg, p.out_col0 + g * 64, m_tile * kTileM + hm * kBlockM + q * 32);
+                        bulk_commit_group();
+                    }
+                }
+            }
+            acc_phase ^= 1;
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // nobody leaves while the peer may still read / signal here
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -430,6 +664,7 @@ struct GemmPlan {
     int block_n, kswz, im2col, stages;
     int cluster;
     int mt;
+    int two_sm;        // CTA-pair (cta_group::2) kernel
     int grid;
     size_t smem;
 };
@@ -470,7 +705,34 @@ cudaError_t launch_t(const GemmPlan *pl, cudaStream_t s, void *out_override, flo
 
 }  // namespace
 
+namespace {
+template <bool IM2COL, int STAGES, int MT>
+cudaError_t launch_2sm(const GemmPlan *pl, cudaStream_t s) {
+    auto kfn = gemm_conv2sm_kernel<IM2COL, STAGES, MT>;
+    constexpr size_t smem = SmemLayout2Sm<STAGES, MT>::kTotal;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl->grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kfn, pl->map_a, pl->map_b, pl->map_out, pl->p);
+}
+}  // namespace
+
 cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    if (pl->two_sm && !out_override && !out2_override) {
+        if (pl->mt == 2) return pl->im2col ? launch_2sm<true, 4, 2>(pl, s) : launch_2sm<false, 4, 2>(pl, s);
+        return pl->im2col ? launch_2sm<true, 7, 1>(pl, s) : launch_2sm<false, 7, 1>(pl, s);
+    }
     if (pl->mt == 2) {      // 256-row CTA tiles
         if (pl->block_n == 128 && pl->kswz == 128)          // 4 stages of 48 KB
             return pl->im2col ? launch_tc<128, 128, true, 4, 1, 2>(pl, s, out_override, out2_override)
@@ -570,6 +832,13 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     const char *cenv = getenv("LWOP_CLUSTER");
     pl->cluster = (cenv && atoi(cenv) == 2 && pl->mt == 1) ? 2 : 1;
     if (p.num_m_tiles < 2) pl->cluster = 1;
+    // CTA-pair kernel (cta_group::2) for the N = 128 convolutions with wide bf16 output; LWOP_2SM=0 disables
+    const char *e2 = getenv("LWOP_2SM");
+    const bool want_2sm = e2 ? atoi(e2) != 0 : true;
+    pl->two_sm = (want_2sm && block_n == 128 && kswz == 128 && d.Cout_pad == 128 && d.Cout == 128 && p.num_m_tiles >= 4 &&
+                  d.out_dtype == LWOP_DT_BF16 && d.out != nullptr && (d.out_col0 % 8) == 0 && (d.ldo % 8) == 0)
+                     ? 1 : 0;
+    if (pl->two_sm) pl->cluster = 2;
     const int work = ((p.num_m_tiles + pl->cluster - 1) / pl->cluster) * p.num_n_tiles;
     const int max_clusters = g_num_sms / pl->cluster;
     pl->grid = (work < max_clusters ? work : max_clusters) * pl->cluster;
