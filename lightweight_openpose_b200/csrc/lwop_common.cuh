@@ -129,9 +129,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug must trap (-> CUDA error the host reports)
-// instead of hanging the GPU box.  ~2^26 probes of a HW-sleeping try_wait is
-// several seconds, far beyond any legitimate wait in these kernels.
+// try_wait with a suspend-time hint: the hardware parks the waiting warp until the phase completes (or this many ns
+// pass) instead of returning at once.  A polling loop issues ~6 instructions per probe and takes issue slots from the
+// warps that share the scheduler with the waiter (measured: ~1/3 of all instructions issued by the fused separable
+// kernel are probes); a parked warp issues nothing but wakes up later.  Which one wins depends on the role: the dense
+// GEMM kernels are faster parked, the depthwise producers / epilogues of the fused kernels are faster polling.
+constexpr uint32_t kMbarSuspendNs = 20000u;
+__device__ __forceinline__ bool mbar_try_wait_park(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
+        : "memory");
+    return ok != 0;
+}
+// Bounded waits: a pipeline bug must trap (-> CUDA error the host reports) instead of hanging the GPU box.
+// 2^26 immediate probes / 2^18 parked probes are several seconds, far beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -140,6 +156,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait_park(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_park(bar, parity)) {
+        if (++spins > (1u << 18)) {
+            printf("lwop: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_sel(uint64_t *bar, uint32_t parity, bool park) {
+    if (park) mbar_wait_park(bar, parity);
+    else mbar_wait(bar, parity);
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const void *desc) {

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const Conv1Para
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(t_empty + kC1Stages);
     float *bias_s = reinterpret_cast<float *>(tmem_ptr + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kC1Stages; ++i) {
             mbar_init(&a_full[i], 8);        // one arrival per producer warp

@@ -42,6 +42,7 @@ struct GemmParams {
     int out_is_f32, act;
     int num_m_tiles, num_n_tiles;
     int use_tma_store;              // wide bf16 output through shared-memory staging + TMA store
+    unsigned park;                  // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 3 epilogue), see mbar_wait_park
 };
 
 template <int BLOCK_N, int KSWZ, int STAGES, int MT>
@@ -89,7 +90,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const int k_blocks = p.taps * p.k_blocks_per_tap;
     // A cluster of CLUSTER CTAs works on CLUSTER consecutive M tiles of the same N tile in lock step:
     // every CTA fetches 1/CLUSTER of the weight (B) tile and multicasts it to its peers, so the L2 -> SM
@@ -147,7 +148,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_sel(&empty_bar[stage], phase ^ 1, p.park & 1u);
                     unsigned char *sa = smem + stage * L::kStageBytes;
                     unsigned char *sb = sa + L::kABytes;
                     mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -185,11 +186,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_wait_sel(&tmem_empty[acc], acc_phase ^ 1, p.park & 2u);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
             for (int kb = 0; kb < k_blocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait_sel(&full_bar[stage], phase, p.park & 2u);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                 const uint32_t sb = sa + L::kABytes;
@@ -231,7 +232,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int m_group = tile / p.num_n_tiles, n_tile = tile - m_group * p.num_n_tiles;
             const int m_tile = m_group * CLUSTER + rank;
             const int n0 = n_tile * BLOCK_N;
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait_sel(&tmem_full[acc], acc_phase, p.park & 8u);
             tcgen05_fence_after();
 #pragma unroll 1
           for (int hm = 0; hm < MT; ++hm) {
@@ -398,7 +399,7 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const int k_blocks = p.taps * p.k_blocks_per_tap;
     const int rank = (int)cluster_ctarank();
     const bool leader = rank == 0;
@@ -451,7 +452,7 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_sel(&empty_bar[stage], phase ^ 1, p.park & 1u);
                     unsigned char *sa = smem + stage * L::kStageBytes;
                     unsigned char *sb = sa + L::kABytes;
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
@@ -480,11 +481,11 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait_sel(&tmem_empty[acc], acc_phase ^ 1, p.park & 2u);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_sel(&full_bar[stage], phase, p.park & 2u);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
@@ -518,7 +519,7 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs, ++local_tile) {
             if ((local_tile & 1) != grp) continue;
             const int m_tile = pt * 2 + rank;
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait_sel(&tmem_full[acc], acc_phase, p.park & 8u);
             tcgen05_fence_after();
 #pragma unroll 1
             for (int hm = 0; hm < MT; ++hm) {
@@ -825,6 +826,10 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     pl->mt = (mt_legal && mt_mode != 1 && (mt_heur || mt_mode == 2)) ? 2 : 1;
     const int tile_m = kBlockM * pl->mt;
     p.num_m_tiles = (int)((M + tile_m - 1) / tile_m);
+    {
+        static const char *pe = getenv("LWOP_GEMM_PARK");
+        p.park = pe ? (unsigned)atoi(pe) : 1u;
+    }
     p.num_n_tiles = d.Cout_pad / block_n;
     // LWOP_CLUSTER=2: clusters of 2 CTAs share each weight tile through TMA multicast.  Measured on B200
     // (profiles/r1_notes.md): no gain -- at cluster size 2 the multicast does not reduce L2->SM traffic,

@@ -62,6 +62,7 @@ struct HpParams {
     int ldc, cat_col_a, cat_col_b;
     float *out_a, *out_b;        // optional fp32 [M][14], [M][26]
     unsigned long long *prof;    // optional stall counters (LWOP_HEADS_PROF=1), nullptr otherwise
+    unsigned park;               // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 3 epilogue)
 };
 
 enum { HP_TOTAL = 0, HP_MMA_X, HP_MMA_ACC1_EMPTY, HP_MMA_W1, HP_MMA_A2_FULL, HP_MMA_W2, HP_MMA_ACC2_EMPTY,
@@ -106,7 +107,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     float *bias1_s = reinterpret_cast<float *>(smem + L::kBias1Off);
     float *bias2_s = reinterpret_cast<float *>(smem + L::kBias2Off);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const int P = p.passes, half = P / 2;
     unsigned long long hp_acc[HP_N];
 #pragma unroll
@@ -148,7 +149,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             int xs = 0, ws = 0;
             uint32_t xph = 0, wph = 0;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-                mbar_wait(&x_empty[xs], xph ^ 1);
+                mbar_wait_sel(&x_empty[xs], xph ^ 1, p.park & 1u);
                 mbar_arrive_expect_tx(&x_full[xs], L::kXBytes);
                 tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
                 tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
@@ -157,7 +158,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     const CUtensorMap *mw = pp < half ? &map_w1a : &map_w1b;
                     const int row0 = (pp < half ? pp : pp - half) * 128;
                     for (int kc = 0; kc < 2; ++kc) {
-                        mbar_wait(&w1_empty[ws], wph ^ 1);
+                        mbar_wait_sel(&w1_empty[ws], wph ^ 1, p.park & 1u);
                         mbar_arrive_expect_tx(&w1_full[ws], L::kW1Bytes);
                         tma_load_2d(smem + L::kW1Off + ws * L::kW1Bytes, mw, &w1_full[ws], kc * 64, row0);
                         if (++ws == kW1Stages) { ws = 0; wph ^= 1; }
@@ -175,7 +176,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     const bool is_a = pp < half;
                     const int k0 = (is_a ? pp : pp - half) * 128;
                     const uint32_t bytes = is_a ? 2 * 16 * 128 : 2 * 32 * 128;
-                    mbar_wait(&w2_empty[ws], wph ^ 1);
+                    mbar_wait_sel(&w2_empty[ws], wph ^ 1, p.park & 1u);
                     mbar_arrive_expect_tx(&w2_full[ws], bytes);
                     unsigned char *dst = smem + L::kW2Off + ws * L::kW2Bytes;
                     tma_load_2d(dst, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0, 0);
@@ -197,10 +198,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         int local_tile = 0;
         auto mma2 = [&](int pp) {
             const int buf = pp & 1;
-            HP_WAIT(HP_MMA_A2_FULL, mbar_wait(&a2_full[buf], (buf ? useb1 : useb0) & 1));
+            HP_WAIT(HP_MMA_A2_FULL, mbar_wait_sel(&a2_full[buf], (buf ? useb1 : useb0) & 1, p.park & 2u));
             fence_proxy_async();           // hidden activations were written with generic-proxy stores
-            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait(acc2_empty, (uint32_t)((local_tile & 1) ^ 1)));
-            HP_WAIT(HP_MMA_W2, mbar_wait(&w2_full[w2s], w2ph));
+            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(acc2_empty, (uint32_t)((local_tile & 1) ^ 1), p.park & 2u));
+            HP_WAIT(HP_MMA_W2, mbar_wait_sel(&w2_full[w2s], w2ph, p.park & 2u));
             tcgen05_fence_after();
             const bool is_a = pp < half;
             const int kslice = is_a ? pp : pp - half;
@@ -225,16 +226,16 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (++w2s == kW2Stages) { w2s = 0; w2ph ^= 1; }
         };
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
-            HP_WAIT(HP_MMA_X, mbar_wait(&x_full[xs], xph));
+            HP_WAIT(HP_MMA_X, mbar_wait_sel(&x_full[xs], xph, p.park & 2u));
             const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
             for (int pp = 0; pp < P; ++pp) {
                 const int s = pp & 1;
-                HP_WAIT(HP_MMA_ACC1_EMPTY, mbar_wait(&acc1_empty[s], ((s ? use1 : use0) & 1) ^ 1));
+                HP_WAIT(HP_MMA_ACC1_EMPTY, mbar_wait_sel(&acc1_empty[s], ((s ? use1 : use0) & 1) ^ 1, p.park & 2u));
                 tcgen05_fence_after();
                 const uint32_t d1 = tmem_base + (uint32_t)(s * 128);
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
-                    HP_WAIT(HP_MMA_W1, mbar_wait(&w1_full[w1s], w1ph));
+                    HP_WAIT(HP_MMA_W1, mbar_wait_sel(&w1_full[w1s], w1ph, p.park & 2u));
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t da = make_kmajor_desc<128>(xa + kc * 16384);
@@ -269,9 +270,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         unsigned char *a2 = smem + L::kA2Off + grp * L::kA2Bytes;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
             for (int pp = grp; pp < P; pp += 2, ++use) {
-                HP_WAIT(HP_E_ACC1_FULL, mbar_wait(&acc1_full[grp], use & 1));
+                HP_WAIT(HP_E_ACC1_FULL, mbar_wait_sel(&acc1_full[grp], use & 1, p.park & 8u));
                 tcgen05_fence_after();
-                HP_WAIT(HP_E_A2_EMPTY, mbar_wait(&a2_empty[grp], (use & 1) ^ 1));   // MMA2 that read this buffer two passes ago retired
+                HP_WAIT(HP_E_A2_EMPTY, mbar_wait_sel(&a2_empty[grp], (use & 1) ^ 1, p.park & 8u));   // MMA2 that read this buffer two passes ago retired
                 const long long hp_e0 = p.prof ? clock64() : 0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
                 const float *b1 = bias1_s + pp * 128;
@@ -311,7 +312,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
             if (grp == 0) {
                 // ---- epilogue-2: the two narrow linear outputs of this tile ----
-                HP_WAIT(HP_E_ACC2_FULL, mbar_wait(acc2_full, (uint32_t)(local_tile & 1)));
+                HP_WAIT(HP_E_ACC2_FULL, mbar_wait_sel(acc2_full, (uint32_t)(local_tile & 1), p.park & 8u));
                 const long long hp_e2 = p.prof ? clock64() : 0;
                 tcgen05_fence_after();
                 uint32_t ra[16], rb[32];
@@ -387,6 +388,10 @@ HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t err
     p.K2 = d.hidden;
     p.passes = 2 * d.hidden / 128;
     p.num_m_tiles = (int)((d.M + 127) / 128);
+    {
+        static const char *pk = getenv("LWOP_HEADS_PARK");
+        p.park = pk ? (unsigned)atoi(pk) : 1u;
+    }
     p.cat = (__nv_bfloat16 *)d.cat; p.ldc = d.ldc; p.cat_col_a = d.cat_col_a; p.cat_col_b = d.cat_col_b;
     p.out_a = d.out_a; p.out_b = d.out_b;
     int sms = gemm_num_sms();

@@ -54,11 +54,12 @@ struct SepParams {
     int k_blocks;                   // C / CB
     int act, ldr, out_col0;
     unsigned long long *prof;       // optional [16] stall counters (LWOP_SEP_PROF=1), nullptr otherwise
+    unsigned park;                  // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 2 depthwise, 3 epilogue)
 };
 
 // stall accounting (debugging aid): cycles one elected thread of each role spends in each barrier wait
 enum { PF_TOTAL = 0, PF_TMA_SLAB_EMPTY, PF_TMA_AB_EMPTY, PF_MMA_TMEM_EMPTY, PF_MMA_B_FULL, PF_MMA_A_FULL,
-       PF_DW_SLAB_FULL, PF_DW_AB_EMPTY, PF_DW_COMPUTE, PF_EPI_TMEM_FULL, PF_EPI_STORE_WAIT, PF_EPI_WORK, PF_N };
+       PF_DW_SLAB_FULL, PF_DW_AB_EMPTY, PF_DW_COMPUTE, PF_EPI_TMEM_FULL, PF_EPI_STORE_WAIT, PF_EPI_WORK, PF_EPI_LDTM, PF_EPI_MATH, PF_EPI_FENCE, PF_N };
 
 #define PF_WAIT(slot, stmt)                                     \
     do {                                                        \
@@ -144,7 +145,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOff);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     constexpr bool pf = PROF;
@@ -195,7 +196,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
-                        PF_WAIT(PF_TMA_AB_EMPTY, mbar_wait(&b_empty[sb], bph ^ 1));
+                        PF_WAIT(PF_TMA_AB_EMPTY, mbar_wait_sel(&b_empty[sb], bph ^ 1, p.park & 1u));
                         mbar_arrive_expect_tx(&b_full[sb], L::kBBytes);
                         tma_load_2d(smem + L::kBOff + sb * L::kBBytes, &map_b, &b_full[sb], kb * CB,
                                     (n_tile * NH + h) * BLOCK_N);
@@ -216,7 +217,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 const int t2 = m_tile - b * tiles_per_img;
                 const int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    PF_WAIT(PF_TMA_SLAB_EMPTY, mbar_wait(&slab_empty[ss], sph ^ 1));
+                    PF_WAIT(PF_TMA_SLAB_EMPTY, mbar_wait_sel(&slab_empty[ss], sph ^ 1, p.park & 1u));
                     unsigned char *slab = smem + L::kSlabOff + ss * L::kSlabBytes;
                     mbar_arrive_expect_tx(&slab_full[ss], L::kSlabTx);
                     tma_load_4d(slab, &map_in, &slab_full[ss], kb * CB, tx * kTW - DIL, ty * kTH - DIL, b);
@@ -237,19 +238,19 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 const int acc = NH == 1 ? (local_tile & 1) : 0;
                 const uint32_t acc_phase = NH == 1 ? (uint32_t)((local_tile >> 1) & 1) : (uint32_t)(local_tile & 1);
                 if (NH == 1) {
-                    PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
+                    PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait_sel(&tmem_empty[acc], acc_phase ^ 1, p.park & 2u));
                     tcgen05_fence_after();
                 }
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    PF_WAIT(PF_MMA_A_FULL, mbar_wait(&a_full[sa], aph));
+                    PF_WAIT(PF_MMA_A_FULL, mbar_wait_sel(&a_full[sa], aph, p.park & 2u));
                     // the A stage was written with ordinary (generic-proxy) stores released through a_full;
                     // this fence makes them visible to the tensor core's async-proxy reads issued below
                     fence_proxy_async();
                     const uint32_t a_addr = smem_u32(smem + L::kAOff + sa * L::kABytes);
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
-                        if (NH == 2 && kb == 0) PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait(&tmem_empty[h], acc_phase ^ 1));
-                        PF_WAIT(PF_MMA_B_FULL, mbar_wait(&b_full[sb], bph));
+                        if (NH == 2 && kb == 0) PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait_sel(&tmem_empty[h], acc_phase ^ 1, p.park & 2u));
+                        PF_WAIT(PF_MMA_B_FULL, mbar_wait_sel(&b_full[sb], bph, p.park & 2u));
                         tcgen05_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)((NH == 1 ? acc : h) * BLOCK_N);
                         const uint32_t b_addr = smem_u32(smem + L::kBOff + sb * L::kBBytes);
@@ -300,7 +301,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
                         for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = make_float2(0.0f, 0.0f);
-                    PF_WAIT(PF_DW_SLAB_FULL, mbar_wait(&slab_full[ss], sph));
+                    PF_WAIT(PF_DW_SLAB_FULL, mbar_wait_sel(&slab_full[ss], sph, p.park & 4u));
                     const long long pf_c0 = pf ? clock64() : 0;
                     const uint32_t sbase = smem_u32(smem + L::kSlabOff + ss * L::kSlabBytes);
                     const uint32_t tbase = sbase + slab_off;
@@ -335,7 +336,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
                     if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
-                    PF_WAIT(PF_DW_AB_EMPTY, mbar_wait(&a_empty[sa], aph ^ 1));   // the MMAs that read this A stage retired
+                    PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));   // the MMAs that read this A stage retired
                     const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes);
 #pragma unroll
                     for (int oy = 0; oy < 4; ++oy)
@@ -373,7 +374,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     acc[r][0] = make_float2(0.0f, 0.0f);
                     acc[r][1] = make_float2(0.0f, 0.0f);
                 }
-                PF_WAIT(PF_DW_SLAB_FULL, mbar_wait(&slab_full[ss], sph));
+                PF_WAIT(PF_DW_SLAB_FULL, mbar_wait_sel(&slab_full[ss], sph, p.park & 4u));
                 const long long pf_c0 = pf ? clock64() : 0;
                 const uint32_t sbase = smem_u32(smem + L::kSlabOff + ss * L::kSlabBytes);
                 const uint32_t tbase = sbase + slab_off;
@@ -408,7 +409,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
                 if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
-                PF_WAIT(PF_DW_AB_EMPTY, mbar_wait(&a_empty[sa], aph ^ 1));   // the MMAs that read this A stage retired
+                PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));   // the MMAs that read this A stage retired
                 const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes) + a_off;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -441,7 +442,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             const int py = ty * kTH + q * 2 + (lane >> 4), px = tx * kTW + (lane & 15);
             const bool row_ok = py < p.H && px < p.W;
             const size_t pix = ((size_t)b * p.H + py) * p.W + px;
-            PF_WAIT(PF_EPI_TMEM_FULL, mbar_wait(&tmem_full[grp], acc_phase));
+            PF_WAIT(PF_EPI_TMEM_FULL, mbar_wait_sel(&tmem_full[grp], acc_phase, p.park & 8u));
             const long long pf_e0 = pf ? clock64() : 0;
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BLOCK_N);
@@ -525,12 +526,394 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------
+// CTA-pair variant with ONE tcgen05.mma per pair (cta_group::2) for Cout = 512: the two CTAs of a cluster process
+// two DIFFERENT pixel patches (M = 256 across the pair) and split every [512 x 64] weight chunk between them:
+// each CTA streams only 128 of the 256 rows of each N half, the tensor cores of both SMs read both halves.  This
+// halves the weight traffic L2 -> SM per output row, which is what bounds the single-CTA form (every 128-pixel
+// tile re-streams the 512 KB weight matrix).  Each CTA runs its own slab loads, depthwise producers and epilogue;
+// the leader CTA's MMA thread issues for the pair once BOTH CTAs' A chunks are ready (each CTA's forwarder thread
+// fences its depthwise warps' stores into the async proxy, then arrives on the leader's barrier).
+// ---------------------------------------------------------------------------
+template <int DIL, int SA_, int SB, int SS>
+struct SepPair2Smem {
+    static constexpr int SA = SA_;                              // >= kKGroup: a K group of 4 chunks is re-read by N half 1
+    static constexpr int kABytes = 128 * 128;
+    static constexpr int kBBytes = 128 * 128;                   // this CTA's 128 rows of one N half of a weight chunk
+    static constexpr int IW = kTW + 2 * DIL, IH = kTH + 2 * DIL;
+    static constexpr int kSlabPix = IW * IH * 64 * 2;
+    static constexpr int kTapBytes = 9 * 64 * 4;
+    static constexpr int kSlabTx = kSlabPix + kTapBytes;
+    static constexpr int kSlabBytes = ((kSlabTx + 127) / 128) * 128;
+    static constexpr int kAOff = 0;
+    static constexpr int kBOff = kAOff + SA * kABytes;
+    static constexpr int kStagingOff = kBOff + SB * kBBytes;
+    static constexpr int kSlabOff = kStagingOff + kEpiWarps * 4096;
+    static constexpr int kBarOff = kSlabOff + SS * kSlabBytes;
+    static constexpr int kNumBars = 2 * SS + 3 * SA + 2 * SB + 4;
+    static constexpr int kBiasOff = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
+    static constexpr int kTotal = kBiasOff + 512 * 4;
+    static_assert(kTotal <= 232448, "shared memory budget exceeded");
+};
+
+template <int DIL, int SA_, int SB, int SS, bool PROF>
+__global__ void __launch_bounds__(kSepThreads, 1)
+sep_pair2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_taps,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                 const SepParams p) {
+    using L = SepPair2Smem<DIL, SA_, SB, SS>;
+    constexpr int KG = 4;                                             // chunks per K group
+    constexpr int CB = 64, KSWZ = 128, BLOCK_N = 256, SA = L::SA;
+    constexpr uint32_t kIdesc = make_idesc_bf16(256, BLOCK_N);        // M = 256 across the pair
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    uint64_t *slab_full = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
+    uint64_t *slab_empty = slab_full + SS;
+    uint64_t *a_ready = slab_empty + SS;          // [SA] local: depthwise warps -> forwarder
+    uint64_t *a_full = a_ready + SA;              // [SA] leader: the forwarders of both CTAs
+    uint64_t *a_empty = a_full + SA;              // [SA] local: multicast commit
+    uint64_t *b_full = a_empty + SA;              // [SB] leader: bytes of both CTAs' loads
+    uint64_t *b_empty = b_full + SB;              // [SB] local: multicast commit
+    uint64_t *tmem_full = b_empty + SB;           // [2]  local: multicast commit (half h)
+    uint64_t *tmem_empty = tmem_full + 2;         // [2]  leader: epilogue warps of both CTAs
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOff);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+    constexpr bool pf = PROF;
+    unsigned long long pf_acc[PROF ? PF_N : 1];
+#pragma unroll
+    for (int i = 0; i < (PROF ? PF_N : 1); ++i) pf_acc[i] = 0;
+    const long long pf_start = PROF ? clock64() : 0;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_pair_tiles = (p.num_m_tiles + 1) >> 1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int kbn = p.k_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_in);
+        tma_prefetch_desc(&map_taps);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SS; ++i) {
+            mbar_init(&slab_full[i], 1);
+            mbar_init(&slab_empty[i], kDwWarps);
+        }
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&a_ready[i], kDwWarps);
+            mbar_init(&a_full[i], 2);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 16);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<512>(tmem_ptr);
+    for (int i = threadIdx.x; i < 512; i += kSepThreads) bias_s[i] = p.bias[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // this CTA's patch of pair tile pt (the last pair may hold a dummy patch: b == B, loads zero-fill, stores clip)
+    auto my_tile = [&](int pt, int &b, int &ty, int &tx) {
+        const int tile = pt * 2 + rank;
+        b = tile / tiles_per_img;
+        const int t2 = tile - b * tiles_per_img;
+        ty = t2 / p.tiles_x;
+        tx = t2 - ty * p.tiles_x;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA: this CTA's 128 rows of each N half of every weight chunk =====================
+        if (lane == 0) {
+            int sb = 0;
+            uint32_t bph = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs)
+                for (int g = 0; g < kbn; g += KG)
+                    for (int h = 0; h < 2; ++h)
+                        for (int kb = g; kb < g + KG; ++kb) {
+                            PF_WAIT(PF_TMA_AB_EMPTY, mbar_wait_sel(&b_empty[sb], bph ^ 1, p.park & 1u));
+                            if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBBytes);
+                            tma_load_2d_2sm(smem + L::kBOff + sb * L::kBBytes, &map_b, &b_full[sb], kb * CB, h * BLOCK_N + rank * 128);
+                            if (++sb == SB) { sb = 0; bph ^= 1; }
+                        }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA: slabs + taps of this CTA's patch =====================
+        if (lane == 0) {
+            int ss = 0;
+            uint32_t sph = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
+                int b, ty, tx;
+                my_tile(pt, b, ty, tx);
+                for (int kb = 0; kb < kbn; ++kb) {
+                    PF_WAIT(PF_TMA_SLAB_EMPTY, mbar_wait_sel(&slab_empty[ss], sph ^ 1, p.park & 1u));
+                    unsigned char *slab = smem + L::kSlabOff + ss * L::kSlabBytes;
+                    mbar_arrive_expect_tx(&slab_full[ss], L::kSlabTx);
+                    tma_load_4d(slab, &map_in, &slab_full[ss], kb * CB, tx * kTW - DIL, ty * kTH - DIL, b);
+                    tma_load_2d(slab + L::kSlabPix, &map_taps, &slab_full[ss], kb * CB, 0);
+                    if (++ss == SS) { ss = 0; sph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== forwarder: own A chunk ready -> visible to the async proxy -> leader's barrier =====================
+        if (lane == 0) {
+            int sa = 0;
+            uint32_t aph = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs)
+                for (int kb = 0; kb < kbn; ++kb) {
+                    mbar_wait_sel(&a_ready[sa], aph, p.park & 1u);
+                    fence_proxy_async();
+                    mbar_arrive_leader(&a_full[sa]);
+                    if (++sa == SA) { sa = 0; aph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, for the pair) =====================
+        if (leader) {
+            // K runs in groups of SA chunks; within a group N half 0 is issued for all SA chunks, then N half 1 re-reads
+            // the same A stages.  Half 0 of a tile therefore completes SA*4 MMAs before half 1 and half 0 of the next
+            // tile starts while half 1 is still being drained: the epilogue overlaps the MMAs although the two halves
+            // fill all 512 TMEM columns.
+            int sb = 0, sa0 = 0;                    // sa0 / aph0: A ring position of the first chunk of the current K group
+            uint32_t aph0 = 0, bph = 0;
+            int local_tile = 0;
+            for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs, ++local_tile) {
+                const uint32_t acc_phase = (uint32_t)(local_tile & 1);
+                for (int g = 0; g < kbn; g += KG) {
+                    for (int h = 0; h < 2; ++h) {
+                        for (int c = 0; c < KG; ++c) {
+                            const int kb = g + c;
+                            int sa = sa0 + c;
+                            uint32_t aph = aph0;
+                            if (sa >= SA) { sa -= SA; aph ^= 1; }
+                            if (kb == 0) PF_WAIT(PF_MMA_TMEM_EMPTY, mbar_wait_sel(&tmem_empty[h], acc_phase ^ 1, p.park & 2u));
+                            if (h == 0) PF_WAIT(PF_MMA_A_FULL, mbar_wait_sel(&a_full[sa], aph, p.park & 2u));
+                            PF_WAIT(PF_MMA_B_FULL, mbar_wait_sel(&b_full[sb], bph, p.park & 2u));
+                            tcgen05_fence_after();
+                            const uint32_t a_addr = smem_u32(smem + L::kAOff + sa * L::kABytes);
+                            const uint32_t b_addr = smem_u32(smem + L::kBOff + sb * L::kBBytes);
+                            if (elect_one()) {
+                                const uint64_t da = make_kmajor_desc<KSWZ>(a_addr);
+                                const uint64_t db = make_kmajor_desc<KSWZ>(b_addr);
+#pragma unroll
+                                for (int k = 0; k < CB / 16; ++k)
+                                    umma_bf16_ss_2sm(tmem_base + (uint32_t)(h * BLOCK_N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                                     kIdesc, (kb | k) != 0 ? 1u : 0u);
+                                umma_commit_2sm(&b_empty[sb], 3);
+                                if (h == 1) umma_commit_2sm(&a_empty[sa], 3);
+                                if (kb == kbn - 1) umma_commit_2sm(&tmem_full[h], 3);
+                            }
+                            __syncwarp();
+                            if (++sb == SB) { sb = 0; bph ^= 1; }
+                        }
+                    }
+                    sa0 += KG;
+                    if (sa0 >= SA) { sa0 -= SA; aph0 ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= kDwWarp0 && warp < kDwWarp0 + kDwWarps) {
+        // ===================== depthwise producers (own patch, every chunk) =====================
+        constexpr int IB = 4 + 2 * DIL;
+        const int wq = warp - kDwWarp0;
+        const int bx = wq & 3, by = wq >> 2;
+        const uint32_t slab_off = (uint32_t)((((by * 4) * L::IW + bx * 4) * CB + lane * 2) * 2);
+        const uint32_t tap_off = (uint32_t)(L::kSlabPix + lane * 8);
+        uint32_t a_col[4];
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox)
+            a_col[ox] = (uint32_t)(((by * 4) * kTW + bx * 4 + ox) * 128 +
+                                   ((((lane >> 2) ^ (((bx & 1) << 2) | ox)) << 4) | ((lane & 3) << 2)));
+        int sa = 0, ss = 0;
+        uint32_t aph = 0, sph = 0;
+        for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs) {
+            for (int kb = 0; kb < kbn; ++kb) {
+                float2 acc[4][4];
+#pragma unroll
+                for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+                    for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = make_float2(0.0f, 0.0f);
+                PF_WAIT(PF_DW_SLAB_FULL, mbar_wait_sel(&slab_full[ss], sph, p.park & 4u));
+                const long long pf_c0 = pf ? clock64() : 0;
+                const uint32_t sbase = smem_u32(smem + L::kSlabOff + ss * L::kSlabBytes);
+                const uint32_t tbase = sbase + slab_off;
+                float2 wt[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint2 v = lds_u64(sbase + tap_off + (uint32_t)(k * CB * 4));
+                    wt[k] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+                }
+#pragma unroll
+                for (int iy = 0; iy < IB; ++iy) {
+                    float2 v[IB];
+#pragma unroll
+                    for (int ix = 0; ix < IB; ++ix) {
+                        uint32_t raw;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(tbase + (uint32_t)((iy * L::IW + ix) * CB * 2)));
+                        v[ix] = unpack_bf16x2_prmt(raw);
+                    }
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int oy = iy - dy * DIL;
+                        if (oy >= 0 && oy < 4) {
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    acc[oy][ox] = ffma2(v[ox + dx * DIL], wt[dy * 3 + dx], acc[oy][ox]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&slab_empty[ss]);
+                if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
+                PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));
+                const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes);
+#pragma unroll
+                for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+                    for (int ox = 0; ox < 4; ++ox)
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(abase + a_col[ox] + (uint32_t)(oy * kTW * 128)),
+                                     "r"(pack_bf16x2(acc[oy][ox].x, acc[oy][ox].y))
+                                     : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[sa]);
+                if (++ss == SS) { ss = 0; sph ^= 1; }
+                if (++sa == SA) { sa = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue: group h drains N half h of this CTA's 128 rows =====================
+        const int q = (warp - kEpiWarp0) & 3;
+        const int grp = (warp - kEpiWarp0) >> 2;
+        unsigned char *stg = smem + L::kStagingOff + (grp * 4 + q) * 4096;
+        int local_tile = 0;
+        for (int pt = pair_id; pt < num_pair_tiles; pt += num_pairs, ++local_tile) {
+            const uint32_t acc_phase = (uint32_t)(local_tile & 1);
+            int b, ty, tx;
+            my_tile(pt, b, ty, tx);
+            const int py = ty * kTH + q * 2 + (lane >> 4), px = tx * kTW + (lane & 15);
+            const bool row_ok = b < p.B && py < p.H && px < p.W;
+            const size_t pix = ((size_t)b * p.H + py) * p.W + px;
+            const long long pf_e0 = pf ? clock64() : 0;
+#pragma unroll 1
+            for (int gg = 0; gg < 4; ++gg) {
+                // N half h = gg / 2 is drained by all 8 warps (this warp: 128 of its 256 columns, 64 per iteration), half 0
+                // first: it completes one K group earlier than half 1 and the next tile's MMAs for it start as soon as it is empty
+                const int h = gg >> 1, g = gg & 1;
+                const int n0 = h * BLOCK_N + grp * (BLOCK_N / 2) + g * 64;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
+                if (g == 0) {
+                    PF_WAIT(PF_EPI_TMEM_FULL, mbar_wait_sel(&tmem_full[h], acc_phase, p.park & 8u));
+                    tcgen05_fence_after();
+                }
+                uint32_t r0[2][32];
+                const long long pf_l0 = pf ? clock64() : 0;
+                tmem_ld_32x32b_x32(taddr, r0[0]);
+                tmem_ld_32x32b_x32(taddr + 32u, r0[1]);
+                const uint4 *rp = (p.residual && row_ok) ? reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + n0) : nullptr;
+                tmem_ld_wait();
+                const long long pf_m0 = pf ? clock64() : 0;
+                if (pf) pf_acc[PF_EPI_LDTM] += (unsigned long long)(pf_m0 - pf_l0);
+                if (g == 1) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty[h]);
+                }
+                uint4 o[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0 + u * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const uint32_t *r = &r0[u][j * 8];
+                        if (p.act == LWOP_ACT_RELU && !p.residual) {
+                            const float2 s0 = fadd2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(b0.x, b0.y));
+                            const float2 s1 = fadd2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(b0.z, b0.w));
+                            const float2 s2 = fadd2(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(b1.x, b1.y));
+                            const float2 s3 = fadd2(make_float2(__uint_as_float(r[6]), __uint_as_float(r[7])), make_float2(b1.z, b1.w));
+                            o[u][j].x = pack_relu_bf16x2(s0.x, s0.y); o[u][j].y = pack_relu_bf16x2(s1.x, s1.y);
+                            o[u][j].z = pack_relu_bf16x2(s2.x, s2.y); o[u][j].w = pack_relu_bf16x2(s3.x, s3.y);
+                        } else {
+                            float v[8];
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = apply_act_fast(__uint_as_float(r[e]) + bb[e], p.act);
+                            if (rp) {
+                                const uint4 rr = rp[u * 4 + j];
+                                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                            }
+                            o[u][j].x = pack_bf16x2(v[0], v[1]); o[u][j].y = pack_bf16x2(v[2], v[3]);
+                            o[u][j].z = pack_bf16x2(v[4], v[5]); o[u][j].w = pack_bf16x2(v[6], v[7]);
+                        }
+                    }
+                }
+                // the previous iteration's TMA stores must have finished READING the staging tiles; that latency hid behind the math
+                if (pf) pf_acc[PF_EPI_MATH] += (unsigned long long)(clock64() - pf_m0);
+                if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());
+                __syncwarp();
+                const long long pf_f0 = pf ? clock64() : 0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(stg + u * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o[u][j];
+                fence_proxy_async();
+                __syncwarp();
+                if (pf) pf_acc[PF_EPI_FENCE] += (unsigned long long)(clock64() - pf_f0);
+                if (lane == 0) {
+                    tma_store_4d(&map_out, stg, p.out_col0 + n0, tx * kTW, ty * kTH + q * 2, b);
+                    tma_store_4d(&map_out, stg + 2048, p.out_col0 + n0 + 32, tx * kTW, ty * kTH + q * 2, b);
+                    bulk_commit_group();
+                }
+            }
+            if (pf) pf_acc[PF_EPI_WORK] += (unsigned long long)(clock64() - pf_e0);
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    if (pf && lane == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == kDwWarp0 || warp == kEpiWarp0)) {
+        if (warp == 0) pf_acc[PF_TOTAL] = (unsigned long long)(clock64() - pf_start);
+#pragma unroll
+        for (int i = 0; i < (PROF ? PF_N : 1); ++i)
+            if (pf_acc[i]) atomicAdd(p.prof + i, pf_acc[i]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm<512>(tmem_base);
+    }
+}
+
 }  // namespace
 
 struct SepPlan {
     CUtensorMap map_in, map_taps, map_b, map_out;
     SepParams p;
     int block_n, cb, dil, nh;
+    int pair;          // CTA-pair kernel (Cout = 512)
     int grid;
 };
 
@@ -578,6 +961,10 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
     pl->block_n = d.Cout_pad % 256 == 0 ? 256 : d.Cout_pad;
     pl->dil = d.dil;
     SepParams &p = pl->p;
+    {
+        static const char *pk = getenv("LWOP_SEP_PARK");
+        p.park = pk ? (unsigned)atoi(pk) : 1u;
+    }
     p.dw_w = d.dw_w;
     p.bias = d.bias;
     p.residual = (const __nv_bfloat16 *)d.residual;
@@ -597,6 +984,15 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
     int sms = gemm_num_sms();
     if (sms <= 0) sms = 148;
     pl->grid = tiles < sms ? tiles : sms;
+    // CTA-pair kernel for Cout = 512 (LWOP_SEP_PAIR=0 keeps the single-CTA NH = 2 form)
+    const char *pe = getenv("LWOP_SEP_PAIR");
+    // Cout = 512: CTA pairs with cta_group::2 MMAs (sep_pair2_kernel) unless LWOP_SEP_PAIR=0 (single-CTA NH = 2 kernel)
+    pl->pair = (pl->nh == 2 && (pe ? atoi(pe) != 0 : true) && p.k_blocks % 4 == 0 && p.num_m_tiles >= 2) ? 1 : 0;
+    if (pl->pair) {
+        const int pair_tiles = (p.num_m_tiles + 1) / 2;
+        const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+        pl->grid = 2 * pairs;
+    }
     {   // input patch + halo: box (CB channels, 16 + 2d columns, 8 + 2d rows, 1 image), zero OOB fill
         cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
         cuuint64_t strides[3] = {(cuuint64_t)d.C * 2, (cuuint64_t)d.W * d.C * 2, (cuuint64_t)d.H * d.W * d.C * 2};
@@ -618,7 +1014,7 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
     {   // pointwise weights [Cout_pad][C] bf16, K-major tiles of (CB, BLOCK_N)
         cuuint64_t dims[2] = {(cuuint64_t)d.C, (cuuint64_t)d.Cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)d.C * 2};
-        cuuint32_t box[2] = {(cuuint32_t)pl->cb, (cuuint32_t)pl->block_n};
+        cuuint32_t box[2] = {(cuuint32_t)pl->cb, (cuuint32_t)(pl->pair ? 128 : pl->block_n)};
         if (!encode_tiled_bf16(&pl->map_b, 2, d.w_packed, dims, strides, box, 2 * pl->cb, err, errlen)) {
             free(pl);
             return nullptr;
@@ -646,7 +1042,7 @@ cudaError_t sep_plan_launch(const SepPlan *pl, cudaStream_t s) {
     // debugging aid: per-role stall cycles, averaged per CTA, printed to stderr (synchronises)
     static const char *names[PF_N] = {"total", "tma:slab_empty", "tma:ab_empty", "mma:tmem_empty", "mma:b_full",
                                       "mma:a_full", "dw:slab_full", "dw:ab_empty", "dw:compute", "epi:tmem_full",
-                                      "epi:store_wait", "epi:work"};
+                                      "epi:store_wait", "epi:work", "epi:ldtm", "epi:math", "epi:fence"};
     unsigned long long *d = nullptr, hbuf[PF_N];
     cudaMalloc(&d, PF_N * sizeof(unsigned long long));
     cudaMemsetAsync(d, 0, PF_N * sizeof(unsigned long long), s);
@@ -663,7 +1059,30 @@ cudaError_t sep_plan_launch(const SepPlan *pl, cudaStream_t s) {
     return e;
 }
 
+template <int DIL, int SA, int SB, int SS>
+static cudaError_t launch_sep_pair2(const SepPlan *pl, cudaStream_t s) {
+    auto kfn = pl->p.prof ? sep_pair2_kernel<DIL, SA, SB, SS, true> : sep_pair2_kernel<DIL, SA, SB, SS, false>;
+    constexpr int smem = SepPair2Smem<DIL, SA, SB, SS>::kTotal;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl->grid);
+    cfg.blockDim = dim3(kSepThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kfn, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+}
+
 static cudaError_t sep_plan_launch_inner(const SepPlan *pl, cudaStream_t s) {
+    // ring depths (A, B, slab): (4,3,3) / (5,3,2) / (4,4,2) measured within 2% of each other
+    if (pl->pair) return pl->dil == 2 ? launch_sep_pair2<2, 4, 3, 2>(pl, s) : launch_sep_pair2<1, 4, 3, 3>(pl, s);
     if (pl->cb == 32) return launch_sep_t<64, 32, 1, 2, 3, 6, 1>(pl, s);
     if (pl->block_n == 128) return launch_sep_t<128, 64, 1, 2, 4, 4, 1>(pl, s);
     if (pl->nh == 2) {
