@@ -12,10 +12,12 @@
 // CTA tile = 128 pixels (rows of the flattened [M, 128] input).  The stacked first layer (N1 = 2*K2 hidden
 // channels) is walked in passes of 128 columns:
 //   MMA1(p)   acc1[p&1] (TMEM, 128 columns)  = X[128x128] * W1[p-th 128 rows]^T          (K = 128)
-//   epilogue-1 (group p&1, 4 warps): tcgen05.ld -> +bias -> ReLU -> bf16 -> written as a K-major 128B-swizzled
-//             A operand into shared memory buffer A2[p&1] (generic-proxy stores released through an mbarrier;
-//             the MMA thread crosses to the async proxy with fence.proxy.async after its acquire)
-//   MMA2(p)   acc2_head (TMEM, 16 or 32 columns) += A2[p&1][128x128] * W2_head[:, p-th K slice]^T
+//   epilogue-1 (group p&1, 4 warps): tcgen05.ld -> +bias -> ReLU -> bf16 -> tcgen05.st back into tensor memory as
+//             the A operand A2[p&1] (64 columns: lane = row, two hidden channels per 32-bit column), released to the
+//             MMA thread through an mbarrier after tcgen05.wait::st
+//   MMA2(p)   acc2_head (TMEM, 16 or 32 columns) += A2[p&1][128x128, TMEM] * W2_head[:, p-th K slice]^T
+//             (tcgen05.mma with the A operand in tensor memory: the hidden activations never touch shared memory,
+//             whose bandwidth the N = 128 MMA1 operand reads already use up)
 // so MMA1(p+1) overlaps epilogue-1(p), and the two epilogue groups alternate passes.
 //   epilogue-2 (group 0): acc2 -> +bias -> fp32 maps and/or the bf16 concat buffer.
 // warp 0: TMA producer for X tiles and W1 chunks; warp 3: TMA producer for W2 slices; warp 1: MMA issuer;
@@ -30,7 +32,7 @@ namespace {
 
 constexpr int kHpThreads = 384;
 constexpr int kHpEpiWarp0 = 4;
-constexpr int kW1Stages = 4;                  // [128 x 64] bf16 chunks, 16 KB each
+constexpr int kW1Stages = 8;                  // [128 x 64] bf16 chunks, 16 KB each
 constexpr int kW2Stages = 2;                  // [<=32 x 128] bf16 slices as two 4 KB K-chunks
 constexpr int kXStages = 2;                   // [128 x 128] bf16 input tiles, 32 KB each
 
@@ -38,11 +40,9 @@ struct HpSmem {
     static constexpr int kXBytes = 2 * 16384;
     static constexpr int kW1Bytes = 16384;
     static constexpr int kW2Bytes = 8192;
-    static constexpr int kA2Bytes = 2 * 16384;
     static constexpr int kXOff = 0;
     static constexpr int kW1Off = kXOff + kXStages * kXBytes;
-    static constexpr int kA2Off = kW1Off + kW1Stages * kW1Bytes;
-    static constexpr int kW2Off = kA2Off + 2 * kA2Bytes;
+    static constexpr int kW2Off = kW1Off + kW1Stages * kW1Bytes;
     static constexpr int kBarOff = kW2Off + kW2Stages * kW2Bytes;
     static constexpr int kNumBars = 2 * kXStages + 2 * kW1Stages + 2 * kW2Stages + 4 + 4 + 2;
     static constexpr int kBias1Off = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
@@ -79,6 +79,7 @@ enum { HP_TOTAL = 0, HP_MMA_X, HP_MMA_ACC1_EMPTY, HP_MMA_W1, HP_MMA_A2_FULL, HP_
     } while (0)
 
 constexpr uint32_t kAcc2ColA = 256, kAcc2ColB = 288;
+constexpr uint32_t kA2TmemCol = 320;           // two 64-column buffers: bf16 hidden activations as the TMEM A operand of MMA2
 
 __global__ void __launch_bounds__(kHpThreads, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1a,
@@ -199,23 +200,22 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         auto mma2 = [&](int pp) {
             const int buf = pp & 1;
             HP_WAIT(HP_MMA_A2_FULL, mbar_wait_sel(&a2_full[buf], (buf ? useb1 : useb0) & 1, p.park & 2u));
-            fence_proxy_async();           // hidden activations were written with generic-proxy stores
             if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(acc2_empty, (uint32_t)((local_tile & 1) ^ 1), p.park & 2u));
             HP_WAIT(HP_MMA_W2, mbar_wait_sel(&w2_full[w2s], w2ph, p.park & 2u));
             tcgen05_fence_after();
             const bool is_a = pp < half;
             const int kslice = is_a ? pp : pp - half;
             const uint32_t d = tmem_base + (is_a ? kAcc2ColA : kAcc2ColB);
-            const uint32_t a2 = smem_u32(smem + L::kA2Off + buf * L::kA2Bytes);
             const uint32_t w2 = smem_u32(smem + L::kW2Off + w2s * L::kW2Bytes);
             if (elect_one()) {
+                // A operand = the hidden activations the epilogue wrote back to tensor memory (no shared-memory round trip)
+                const uint32_t a2t = tmem_base + kA2TmemCol + (uint32_t)(buf * 64);
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
-                    const uint64_t da = make_kmajor_desc<128>(a2 + kc * 16384);
                     const uint64_t db = make_kmajor_desc<128>(w2 + kc * 4096);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
+                        umma_bf16_ts(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
                                      (kslice | kc | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&a2_empty[buf]);
@@ -267,7 +267,6 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int row = q * 32 + lane;                        // row of the tile == TMEM lane
         uint32_t use = 0;
         int local_tile = 0;
-        unsigned char *a2 = smem + L::kA2Off + grp * L::kA2Bytes;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
             for (int pp = grp; pp < P; pp += 2, ++use) {
                 HP_WAIT(HP_E_ACC1_FULL, mbar_wait_sel(&acc1_full[grp], use & 1, p.park & 8u));
@@ -287,7 +286,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         if (lane == 0) mbar_arrive(&acc1_empty[grp]);
                     }
                     const float4 *bs4 = reinterpret_cast<const float4 *>(b1 + c * 32);
-                    unsigned char *dst = a2 + (c >> 1) * 16384 + row * 128;
+                    uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 b0 = bs4[2 * j], bq = bs4[2 * j + 1];
@@ -302,10 +301,13 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         uint4 o;
                         o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
                         o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
-                        // K-major 128B swizzle: 16-byte chunk ((c & 1) * 4 + j) XOR (row & 7)
-                        *reinterpret_cast<uint4 *>(dst + (((((c & 1) << 2) | j) ^ (row & 7)) << 4)) = o;
+                        pk[j * 4 + 0] = o.x; pk[j * 4 + 1] = o.y; pk[j * 4 + 2] = o.z; pk[j * 4 + 3] = o.w;
                     }
+                    // TMEM A operand of MMA2: lane = row, hidden column k of this pass in 32-bit column k / 2
+                    tmem_st_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kA2TmemCol + (uint32_t)(grp * 64 + c * 16), pk);
                 }
+                tmem_st_wait();
+                tcgen05_fence_before();
                 __syncwarp();                                  // orders the lanes' stores before lane 0's release
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if (p.prof) hp_acc[HP_E1_WORK] += (unsigned long long)(clock64() - hp_e0);
