@@ -297,6 +297,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t cta_mask
         : "memory");
 }
 
+// ---- programmatic dependent launch ----
+// Kernels of the forward chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next
+// kernel's CTAs may become resident and run their prologue (barrier init, TMEM allocation, descriptor prefetch, bias /
+// tap loads -- none of which depend on the previous kernel) while the previous kernel drains.  pdl_wait() blocks until
+// the previous kernel has completed and its writes are visible; nothing that kernel produced may be read and nothing
+// it reads may be written before it.  pdl_launch_dependents() lets the NEXT kernel start its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- tcgen05 ----
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -280,6 +280,8 @@ conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, in
         for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)((double)i / 255.0);
         __syncthreads();
     }
+    pdl_wait();                  // first kernel of the forward chain: the previous step's readers of `out` are done
+    pdl_launch_dependents();
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * Ho * Wo;
     if (p >= total) return;
@@ -325,12 +327,10 @@ cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, in
     long long total = (long long)B * ph.out * pw.out;
     unsigned grid = (unsigned)((total + 127) / 128);
     if (in_is_u8)
-        conv1_bf16_kernel<uint8_t><<<grid, 128, 0, s>>>((const uint8_t *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
-                                                        ph.before, pw.before);
-    else
-        conv1_bf16_kernel<float><<<grid, 128, 0, s>>>((const float *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
-                                                      ph.before, pw.before);
-    return cudaGetLastError();
+        return launch_chain(conv1_bf16_kernel<uint8_t>, grid, 128, 0, s, 1, (const uint8_t *)in, (uint4 *)out, B, H, W, ph.out,
+                            pw.out, ph.before, pw.before);
+    return launch_chain(conv1_bf16_kernel<float>, grid, 128, 0, s, 1, (const float *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
+                        ph.before, pw.before);
 }
 
 // uint8 frame -> float32 / 255 (reference test&eval/model_test.py:65 `img_data / 255.`:

@@ -77,6 +77,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwParams p) {
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_wait();                  // the previous kernel of the chain has completed
+    pdl_launch_dependents();
 
     auto issue = [&](int sp, int buf) {
         const int tx = sp % p.tiles_x;
@@ -174,8 +176,7 @@ cudaError_t launch_dw_t(const DwPlan *pl, cudaStream_t s) {
     auto kfn = dw_tma_kernel<STRIDE, DIL, CB, TW, TH>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem);
     if (e != cudaSuccess) return e;
-    kfn<<<pl->grid, kDwThreads, G::kSmem, s>>>(pl->map_in, pl->p);
-    return cudaGetLastError();
+    return launch_chain(kfn, (unsigned)pl->grid, kDwThreads, G::kSmem, s, 1, pl->map_in, pl->p);
 }
 
 // resident CTAs per SM of the instantiation a plan will launch

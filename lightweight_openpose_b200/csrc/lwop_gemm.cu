@@ -124,6 +124,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (CLUSTER > 1) cluster_sync_all();               // peers' barriers are initialised before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
+    pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -429,6 +431,8 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     cluster_sync_all();                              // the peer's barriers exist before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
+    pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
@@ -627,6 +631,10 @@ bool gemm_driver_ready(char *err, size_t errlen) {
 }
 
 int gemm_num_sms() { return g_num_sms; }
+bool pdl_enabled() {
+    static const bool on = !(getenv("LWOP_PDL") && atoi(getenv("LWOP_PDL")) == 0);
+    return on;
+}
 
 bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,
                        const cuuint64_t *strides_bytes, const cuuint32_t *box, int swizzle_bytes, char *err,
@@ -683,19 +691,7 @@ cudaError_t launch_tc(const GemmPlan *pl, cudaStream_t s, void *out_override, fl
     if (out_override) p.out = out_override;
     if (out2_override) p.out2 = out2_override;
     if (out_override) p.use_tma_store = 0;         // the store map is bound to the plan's own output
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)pl->grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kfn, pl->map_a, pl->map_b, pl->map_out, p);
+    return launch_chain(kfn, (unsigned)pl->grid, kNumThreads, smem, s, CLUSTER, pl->map_a, pl->map_b, pl->map_out, p);
 }
 
 template <int BLOCK_N, int KSWZ, bool IM2COL, int STAGES>
@@ -713,19 +709,7 @@ cudaError_t launch_2sm(const GemmPlan *pl, cudaStream_t s) {
     constexpr size_t smem = SmemLayout2Sm<STAGES, MT>::kTotal;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)pl->grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kfn, pl->map_a, pl->map_b, pl->map_out, pl->p);
+    return launch_chain(kfn, (unsigned)pl->grid, kNumThreads, smem, s, 2, pl->map_a, pl->map_b, pl->map_out, pl->p);
 }
 }  // namespace
 

@@ -143,6 +143,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
+    pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     if (warp == 0) {
         // ===================== TMA producer: input tiles + first-layer weight chunks =====================
@@ -454,9 +456,8 @@ cudaError_t head_pair_plan_launch(const HeadPairPlan *pl, cudaStream_t s, float 
         fprintf(stderr, "\n");
         return cudaGetLastError();
     }
-    head_pair_kernel<<<pl->grid, kHpThreads, HpSmem::kTotal, s>>>(pl->map_x, pl->map_w1a, pl->map_w1b, pl->map_w2a,
-                                                                 pl->map_w2b, p);
-    return cudaGetLastError();
+    return launch_chain(head_pair_kernel, (unsigned)pl->grid, kHpThreads, HpSmem::kTotal, s, 1, pl->map_x, pl->map_w1a, pl->map_w1b,
+                        pl->map_w2a, pl->map_w2b, p);
 }
 
 }  // namespace lwop

@@ -66,6 +66,34 @@ void gemm_plan_destroy(GemmPlan *p);
 cudaError_t gemm_plan_launch(const GemmPlan *p, cudaStream_t s, void *out_override = nullptr,
                              float *out2_override = nullptr);
 bool gemm_driver_ready(char *err, size_t errlen);
+// launch with the programmatic-dependent-launch attribute (unless LWOP_PDL=0) and an optional cluster width
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kfn)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, int cluster_x,
+                                Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kfn, static_cast<KArgs>(args)...);
+}
 int gemm_num_sms();
 // cuTensorMapEncodeTiled for a bf16 tensor (rank 2..4), no interleave, zero OOB fill
 bool encode_tiled_bf16(CUtensorMap *map, int rank, const void *base, const cuuint64_t *dims,

@@ -185,6 +185,8 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
+    pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     if (warp == 0) {
         // ===================== TMA producer: pointwise weight tiles (B ring) =====================
@@ -630,6 +632,8 @@ sep_pair2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
+    pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     // this CTA's patch of pair tile pt (the last pair may hold a dummy patch: b == B, loads zero-fill, stores clip)
     auto my_tile = [&](int pt, int &b, int &ty, int &tx) {
@@ -926,14 +930,12 @@ cudaError_t launch_sep_t(const SepPlan *pl, cudaStream_t s) {
         auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, true>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        kfn<<<pl->grid, kSepThreads, smem, s>>>(pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
-        return cudaGetLastError();
+        return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
     }
     auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, false>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kfn<<<pl->grid, kSepThreads, smem, s>>>(pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
-    return cudaGetLastError();
+    return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
 }
 
 }  // namespace
@@ -1065,19 +1067,7 @@ static cudaError_t launch_sep_pair2(const SepPlan *pl, cudaStream_t s) {
     constexpr int smem = SepPair2Smem<DIL, SA, SB, SS>::kTotal;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)pl->grid);
-    cfg.blockDim = dim3(kSepThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kfn, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+    return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 2, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
 }
 
 static cudaError_t sep_plan_launch_inner(const SepPlan *pl, cudaStream_t s) {
