@@ -496,7 +496,7 @@ limbs_kernel(const float *__restrict__ paf, int h, int w, int H, int W, double t
 // ---------------------------------------------------------------------------
 // K3: per image (one warp): joint list, greedy grouping, keypoint table.
 // ---------------------------------------------------------------------------
-constexpr int kSmemPersons = 160;   // working persons kept in shared memory; the rest spill to the global scratch
+constexpr int kSmemPersons = 128;   // working persons kept in shared memory; the rest spill to the global scratch
 
 __global__ void __launch_bounds__(32)
 group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_counts, const double *__restrict__ limbs,
@@ -506,41 +506,60 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     // working list of persons before the final filter: at most one new person per connection
     __shared__ double Ps[kSmemPersons][16];
     __shared__ float s_score[LWOP_MAX_JOINTS];           // joint scores (float32 values, exact in float)
-    __shared__ double s_conn[LWOP_MAX_PEAKS][3];         // (src_id, dst_id, score) of the current limb type
+    __shared__ double s_cs[LWOP_MAX_PEAKS];              // connection scores of the current limb type
+    __shared__ short s_ca[LWOP_MAX_PEAKS], s_cb[LWOP_MAX_PEAKS];   // their (src_id, dst_id)
+    // columns ja / jb of every working person for the current limb type, as integers: the membership test of the
+    // serial loop (:329-331) reads these instead of two doubles per person; kept in step with the rows below
+    __shared__ short s_pa[kMaxWorkPersons], s_pb[kMaxWorkPersons];
     __shared__ int s_off[LWOP_NUM_JOINTS + 1];
     __shared__ float s_x[LWOP_MAX_JOINTS], s_y[LWOP_MAX_JOINTS];   // joint coordinates for the keypoint table
     __shared__ unsigned char s_type[LWOP_MAX_JOINTS];
     double *Pg = work + (long long)b * kMaxWorkPersons * 16;
-    auto P = [&](int k) -> double * { return k < kSmemPersons ? Ps[k] : Pg + (long long)(k - kSmemPersons) * 16; };
+    // explicit address spaces (a generic pointer would turn the shared-memory accesses into generic loads)
+    auto row_ld = [&](int k, int c) -> double { return k < kSmemPersons ? Ps[k][c] : Pg[(long long)(k - kSmemPersons) * 16 + c]; };
+    auto row_st = [&](int k, int c, double v) {
+        if (k < kSmemPersons) Ps[k][c] = v;
+        else Pg[(long long)(k - kSmemPersons) * 16 + c] = v;
+    };
 
     const int *pc = peak_counts + b * 16;
     int *cnt = counts + b * LWOP_COUNTS;
-    if (lane == 0) {
-        int acc = 0;
-        for (int c = 0; c < LWOP_NUM_JOINTS; ++c) {
-            s_off[c] = acc;
-            cnt[4 + c] = pc[c];
-            acc += pc[c];
+    const int my_pc = lane < LWOP_NUM_JOINTS ? pc[lane] : 0;
+    const int my_nconn = lane < LWOP_NUM_LIMBS ? cnt[18 + lane] : 0;
+    {   // exclusive prefix sum of the per-type peak counts
+        int incl = my_pc;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
-        s_off[LWOP_NUM_JOINTS] = acc;
-        cnt[0] = acc;
+        if (lane < LWOP_NUM_JOINTS) {
+            s_off[lane] = incl - my_pc;
+            cnt[4 + lane] = my_pc;
+        }
+        if (lane == LWOP_NUM_JOINTS - 1) {
+            s_off[LWOP_NUM_JOINTS] = incl;
+            cnt[0] = incl;
+        }
     }
     __syncwarp();
     double *jl = joints + (long long)b * LWOP_MAX_JOINTS * 6;
     for (int c = 0; c < LWOP_NUM_JOINTS; ++c) {                   // (x, y, score, id, 0, type) (:481-482)
         const float *pk = peaks + ((long long)b * LWOP_NUM_JOINTS + c) * LWOP_MAX_PEAKS * 4;
-        for (int i = lane; i < pc[c]; i += 32) {
+        const int n = __shfl_sync(0xffffffffu, my_pc, c);
+        for (int i = lane; i < n; i += 32) {
             const int id = s_off[c] + i;
+            const float4 pv = *reinterpret_cast<const float4 *>(pk + i * 4);
             double *o = jl + (long long)id * 6;
-            o[0] = pk[i * 4 + 0];
-            o[1] = pk[i * 4 + 1];
-            o[2] = pk[i * 4 + 2];
+            o[0] = pv.x;
+            o[1] = pv.y;
+            o[2] = pv.z;
             o[3] = (double)id;
             o[4] = 0.0;
             o[5] = (double)c;
-            s_score[id] = pk[i * 4 + 2];
-            s_x[id] = pk[i * 4 + 0];
-            s_y[id] = pk[i * 4 + 1];
+            s_score[id] = pv.z;
+            s_x[id] = pv.x;
+            s_y[id] = pv.y;
             s_type[id] = (unsigned char)c;
         }
     }
@@ -550,69 +569,102 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     bool overflow = false;
     for (int t = 0; t < LWOP_NUM_LIMBS; ++t) {
         const int ja = c_limb_src[t], jb = c_limb_dst[t];
-        const int nconn = cnt[18 + t];
+        const int nconn = __shfl_sync(0xffffffffu, my_nconn, t);
         total_conn += nconn;
         const double *rows = limbs + ((long long)b * LWOP_NUM_LIMBS + t) * LWOP_MAX_PEAKS * 5;
-        for (int e = lane; e < nconn * 3; e += 32) s_conn[e / 3][e % 3] = rows[(e / 3) * 5 + (e % 3)];
+        for (int e = lane; e < nconn; e += 32) {
+            s_ca[e] = (short)rows[e * 5 + 0];
+            s_cb[e] = (short)rows[e * 5 + 1];
+            s_cs[e] = rows[e * 5 + 2];
+        }
+        for (int k = lane; k < np; k += 32) {                     // this type's two columns of every working person
+            s_pa[k] = (short)row_ld(k, ja);
+            s_pb[k] = (short)row_ld(k, jb);
+        }
         __syncwarp();
         for (int r = 0; r < nconn; ++r) {
-            const double a_id = s_conn[r][0], b_id = s_conn[r][1], s = s_conn[r][2];
-            // persons that already hold one of the two joints (:329-331)
+            const int a_id = s_ca[r], b_id = s_cb[r];
+            const double s = s_cs[r];
+            // persons that already hold one of the two joints (:329-331), in list order
             int nm = 0, m0 = -1, m1 = -1;
             for (int base = 0; base < np; base += 32) {
                 const int k = base + lane;
-                bool hit = false;
-                if (k < np) {
-                    const double *row = P(k);
-                    hit = row[ja] == a_id || row[jb] == b_id;
-                }
+                const bool hit = k < np && (s_pa[k] == a_id || s_pb[k] == b_id);
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int bit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (nm == 0) m0 = base + bit;
-                    else if (nm == 1) m1 = base + bit;
-                    ++nm;
+                if (mask) {
+                    if (nm == 0) {
+                        m0 = base + __ffs(mask) - 1;
+                        const unsigned rest = mask & (mask - 1);
+                        if (rest) m1 = base + __ffs(rest) - 1;
+                    } else if (nm == 1) {
+                        m1 = base + __ffs(mask) - 1;
+                    }
+                    nm += __popc(mask);
                 }
             }
-            const double js_b = (double)s_score[(int)b_id];
+            const double js_b = (double)s_score[b_id];
+            const double bd = (double)b_id;
             if (nm == 1) {                                        // (:336-347)
-                double *p0 = P(m0);
-                if (lane == 0 && p0[jb] != b_id) {
-                    p0[jb] = b_id;
-                    p0[15] += 1.0;
-                    p0[14] += __dadd_rn(js_b, s);
+                if (lane == 0 && s_pb[m0] != b_id) {
+                    row_st(m0, jb, bd);
+                    row_st(m0, 15, row_ld(m0, 15) + 1.0);
+                    row_st(m0, 14, row_ld(m0, 14) + __dadd_rn(js_b, s));
+                    s_pb[m0] = (short)b_id;
                 }
             } else if (nm == 2) {                                 // (:348-366)
-                double *p0 = P(m0), *p1 = P(m1);
-                bool share = false;
-                if (lane < 14) share = p0[lane] >= 0.0 && p1[lane] >= 0.0;
-                share = __any_sync(0xffffffffu, share);
+                double v0 = 0.0, v1 = 0.0;
+                if (lane < 16) {
+                    v0 = row_ld(m0, lane);
+                    v1 = row_ld(m1, lane);
+                }
+                const bool share = __any_sync(0xffffffffu, lane < 14 && v0 >= 0.0 && v1 >= 0.0);
                 if (!share) {
-                    if (lane < 14) p0[lane] += __dadd_rn(p1[lane], 1.0);
-                    if (lane == 14) p0[14] = __dadd_rn(__dadd_rn(p0[14], p1[14]), s);
-                    if (lane == 15) p0[15] += p1[15];
+                    if (lane < 14) v0 += __dadd_rn(v1, 1.0);
+                    if (lane == 14) v0 = __dadd_rn(__dadd_rn(v0, v1), s);
+                    if (lane == 15) v0 += v1;
+                    if (lane < 16) row_st(m0, lane, v0);
+                    if (lane == ja) s_pa[m0] = (short)v0;
+                    if (lane == jb) s_pb[m0] = (short)v0;
                     __syncwarp();
-                    for (int k = m1; k + 1 < np; ++k) {           // list.pop(m1)
-                        double v = 0.0;
-                        if (lane < 16) v = P(k + 1)[lane];
-                        if (lane < 16) P(k)[lane] = v;
+                    // list.pop(m1): rows and column caches move up by one, 32 persons per step (read all, then write all)
+                    for (int base = m1; base + 1 < np; base += 32) {
+                        const int k = base + lane;
+                        const bool live = k + 1 < np;
+                        double rv[16];
+                        short ca = 0, cb = 0;
+                        if (live) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) rv[c] = row_ld(k + 1, c);
+                            ca = s_pa[k + 1];
+                            cb = s_pb[k + 1];
+                        }
+                        __syncwarp();
+                        if (live) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) row_st(k, c, rv[c]);
+                            s_pa[k] = ca;
+                            s_pb[k] = cb;
+                        }
                         __syncwarp();
                     }
                     --np;
                 } else if (lane == 0) {
-                    p0[jb] = b_id;
-                    p0[15] += 1.0;
-                    p0[14] += __dadd_rn(js_b, s);
+                    row_st(m0, jb, bd);
+                    row_st(m0, 15, row_ld(m0, 15) + 1.0);
+                    row_st(m0, 14, row_ld(m0, 14) + __dadd_rn(js_b, s));
+                    s_pb[m0] = (short)b_id;
                 }
             } else {                                              // 0 or >= 3 matches: new person (:367-379)
                 if (np < kMaxWorkPersons) {
-                    double *pn = P(np);
-                    if (lane < 14) pn[lane] = lane == ja ? a_id : (lane == jb ? b_id : -1.0);
-                    if (lane == 15) pn[15] = 2.0;
+                    if (lane < 14) row_st(np, lane, lane == ja ? (double)a_id : (lane == jb ? bd : -1.0));
+                    if (lane == 15) row_st(np, 15, 2.0);
                     if (lane == 14) {
-                        const double js_a = (double)s_score[(int)a_id];
-                        pn[14] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, js_a), js_b), s);
+                        const double js_a = (double)s_score[a_id];
+                        row_st(np, 14, __dadd_rn(__dadd_rn(__dadd_rn(0.0, js_a), js_b), s));
+                    }
+                    if (lane == 0) {
+                        s_pa[np] = (short)a_id;
+                        s_pb[np] = (short)b_id;
                     }
                     ++np;
                 } else {
@@ -627,19 +679,19 @@ group_kernel(const float *__restrict__ peaks, const int *__restrict__ peak_count
     float *ko = keypoints + (long long)b * LWOP_MAX_PERSONS * 42;
     int kept = 0;
     for (int k = 0; k < np; ++k) {
-        const double *row = P(k);
-        const bool drop = row[15] < 3.0 || (row[14] / row[15]) < 0.2;
+        const double r15 = row_ld(k, 15);
+        const bool drop = r15 < 3.0 || (row_ld(k, 14) / r15) < 0.2;
         if (drop) continue;
         if (kept >= LWOP_MAX_PERSONS) {
             overflow = true;
             break;
         }
-        if (lane < 16) po[kept * 16 + lane] = row[lane];
+        if (lane < 16) po[kept * 16 + lane] = row_ld(k, lane);
         for (int e = lane; e < 42; e += 32) ko[kept * 42 + e] = 0.0f;
         __syncwarp();
         if (lane == 0) {
             for (int t = 0; t < LWOP_NUM_LIMBS; ++t) {
-                const double ia = row[c_limb_src[t]], ib = row[c_limb_dst[t]];
+                const double ia = row_ld(k, c_limb_src[t]), ib = row_ld(k, c_limb_dst[t]);
                 if (ia < 0.0 || ib < 0.0) continue;               // `-1 in joint_indices` (:411)
                 const double ids[2] = {ia, ib};
                 for (int e = 0; e < 2; ++e) {

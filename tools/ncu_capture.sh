@@ -6,12 +6,12 @@ TAG=${1:-r1}
 OUT=gpurun_out
 python tools/profile_forward.py 256 2 > $OUT/fwd_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/fwd_plain.log; exit 1; }
 COMMON="--set full --clock-control none --import-source on --kernel-name-base demangled"
-# fused separable, Cout = 512 (NH = 2 instantiation, dil 1): 2nd launch of the 2nd forward (= layer 9)
-timeout 400 ncu $COMMON -k 'regex:sep_conv_kernel<\(int\)256, \(int\)64, \(int\)1, \(int\)2, \(int\)3, \(int\)3, \(int\)2' -s 6 -c 1 -o $OUT/${TAG}_sep512 -f python tools/profile_forward.py 256 2 > $OUT/ncu_sep512.log 2>&1
+# fused separable, Cout = 512 on CTA pairs (cta_group::2), dil 1: 2nd launch of the 2nd forward (= layer 9)
+timeout 400 ncu $COMMON -k 'regex:sep_pair2_kernel<\(int\)1' -s 6 -c 1 -o $OUT/${TAG}_sep512 -f python tools/profile_forward.py 256 2 > $OUT/ncu_sep512.log 2>&1
 # fused separable, first layer (32 -> 64 at 184x184, HBM-bound)
 timeout 400 ncu $COMMON -k 'regex:sep_conv_kernel<\(int\)64' -s 1 -c 1 -o $OUT/${TAG}_sep32 -f python tools/profile_forward.py 256 2 > $OUT/ncu_sep32.log 2>&1
-# dense 3x3 128->128 (im2col): first of the 2nd forward
-timeout 400 ncu $COMMON -k 'regex:gemm_conv_kernel<\(int\)128, \(int\)128, \(bool\)1' -s 14 -c 1 -o $OUT/${TAG}_conv3x3 -f python tools/profile_forward.py 256 2 > $OUT/ncu_c3.log 2>&1
+# dense 3x3 128->128 (im2col, CTA-pair kernel): first of the 2nd forward
+timeout 400 ncu $COMMON -k 'regex:gemm_conv2sm_kernel<\(bool\)1' -s 14 -c 1 -o $OUT/${TAG}_conv3x3 -f python tools/profile_forward.py 256 2 > $OUT/ncu_c3.log 2>&1
 # fused head pair (initial stage, hidden 512)
 timeout 400 ncu $COMMON -k 'regex:head_pair_kernel' -s 2 -c 1 -o $OUT/${TAG}_heads -f python tools/profile_forward.py 256 2 > $OUT/ncu_heads.log 2>&1
 ls -la $OUT/${TAG}_*.ncu-rep
