@@ -134,14 +134,20 @@ def cpu_path_images_per_s(n_images: int, threads: int):
     return n_images / dt, dt
 
 
+def workload_name(batch: int, world: int) -> str:
+    """config.workload, shared by both arms so the driver compares like with like."""
+    return (f"batch {batch} per GPU, 368x368 forward+decode (BASELINE.json configs[2]), "
+            f"{world} independent replica(s), no collective on the data path")
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(2, min(args.cpu_images, 160 // max(args.steps, 1)))     # keep the whole run to a few minutes
+    sample = max(2, min(args.cpu_images, 1600 // max(args.steps + args.warmup, 1)))     # whole run: <= ~90 s of CPU work
     vals = []
     for _ in range(args.warmup):
-        cpu_path_images_per_s(1, threads)
+        cpu_path_images_per_s(sample, threads)
     t_total = 0.0
     for _ in range(args.steps):
         v, dt = cpu_path_images_per_s(sample, threads)
@@ -152,10 +158,12 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"368x368 forward+decode, batch-1 serial loop over {sample} synthetic frames per step "
-                               "(CPU port of the reference path: torch-CPU fp32 forward, all host threads, + "
-                               "numpy/cv2 decode, single thread as in the reference loop); stand-in for TF-CPU, "
-                               "TensorFlow is not installable here"},
+        "config": {"workload": workload_name(args.batch, world), "global_batch": args.batch * world, "height": H,
+                   "width": W, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
+                   "reference_arm": f"bounded sample of that workload: each step is the reference's batch-1 serial "
+                                    f"loop (model_test.py:82-99) over {sample} of its frames; CPU port of the reference "
+                                    "path (torch-CPU fp32 forward on all host threads + numpy/cv2 decode, one thread "
+                                    "as in the reference loop), stand-in for TF-CPU: TensorFlow is not installable here"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} frames x {args.steps} steps"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -420,8 +428,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"batch {batch} per GPU, 368x368 forward+decode (BASELINE.json configs[2]), "
-                            f"{world} independent replica(s), no collective on the data path",
+                "workload": workload_name(batch, world),
                 "global_batch": batch * world, "height": H, "width": W, "mode": args.mode,
                 "weights": source, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
                 "l2": f"inputs {x_dev.numel() * 4 / 2**20:.0f} MiB fp32 per step > 126 MB L2 (no flush needed)",
@@ -472,7 +479,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
-    ap.add_argument("--cpu-images", type=int, default=16, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=224,
+                    help="frames in the bounded CPU-baseline sample (~11 s at ~20 images/s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="separable layers as two kernels (A/B timing of the fusion)")
     ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage of the host-buffer path (0 = library default)")
