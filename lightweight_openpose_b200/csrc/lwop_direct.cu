@@ -261,6 +261,8 @@ cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s) {
 // the constant bank (no shared-memory or register traffic for the 864 taps).
 __constant__ float c_conv1_w[27 * 32];
 __constant__ float c_conv1_b[32];
+// uint8 -> float32(u8 / 255.0) table (the reference's `img / 255.` in float64, fed as float32), filled by the host
+__device__ float g_u8_lut[256];
 
 cudaError_t set_conv1_constants(const float *w_host_n27 /*[32][27]*/, const float *b_host /*[32]*/) {
     float t[27 * 32];
@@ -268,63 +270,91 @@ cudaError_t set_conv1_constants(const float *w_host_n27 /*[32][27]*/, const floa
         for (int k = 0; k < 27; ++k) t[k * 32 + n] = w_host_n27[n * 27 + k];
     cudaError_t e = cudaMemcpyToSymbol(c_conv1_w, t, sizeof(t));
     if (e != cudaSuccess) return e;
+    float lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);
+    e = cudaMemcpyToSymbol(g_u8_lut, lut, sizeof(lut));
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_conv1_b, b_host, 32 * sizeof(float));
 }
 
+// Two horizontally adjacent output pixels per thread: every 128-bit weight load from the constant bank feeds both,
+// and the 864 multiply-adds of a pixel issue as 432 packed FFMA2 (scalar input broadcast x uniform-register weight
+// pair, accumulator pair = two adjacent output channels).  Each output keeps its 27-step accumulation order.
 template <typename TIn>
 __global__ void __launch_bounds__(128)
 conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int Ho, int Wo,
                   int pad_t, int pad_l) {
-    __shared__ float lut[256];   // uint8 -> float32(u8 / 255.0), the reference's `img / 255.`
+    __shared__ float lut[256];
     if (sizeof(TIn) == 1) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)((double)i / 255.0);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_u8_lut[i];
         __syncthreads();
     }
     pdl_wait();                  // first kernel of the forward chain: the previous step's readers of `out` are done
     pdl_launch_dependents();
+    const int wp = (Wo + 1) >> 1;                   // pixel pairs per output row
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * Ho * Wo;
+    long long total = (long long)B * Ho * wp;
     if (p >= total) return;
-    int ox = (int)(p % Wo);
-    long long t = p / Wo;
-    int oy = (int)(t % Ho);
-    int b = (int)(t / Ho);
-    float acc[32];
+    const int ox = (int)(p % wp) * 2;
+    long long t = p / wp;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const bool two = ox + 1 < Wo;
+    float2 acc[2][16];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = c_conv1_b[n];
+    for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = make_float2(c_conv1_b[2 * n], c_conv1_b[2 * n + 1]);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
         const int iy = oy * 2 - pad_t + dy;
         const bool yok = iy >= 0 && iy < H;
+        const TIn *rowp = in + ((long long)b * H + (yok ? iy : 0)) * W * 3;
+        // the two windows share one input column: 5 columns x 3 channels per row
+        float v[5][3];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int ix = ox * 2 - pad_l + dx;
+        for (int cx = 0; cx < 5; ++cx) {
+            const int ix = ox * 2 - pad_l + cx;
             const bool ok = yok && ix >= 0 && ix < W;
-            const TIn *ip = in + (((long long)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
+            const TIn *ip = rowp + (ok ? ix : 0) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float v = 0.0f;
-                if (ok) v = sizeof(TIn) == 1 ? lut[(int)ip[c]] : (float)ip[c];
-#pragma unroll
-                for (int n = 0; n < 32; ++n) acc[n] = fmaf(v, c_conv1_w[((dy * 3 + dx) * 3 + c) * 32 + n], acc[n]);
+                float x = 0.0f;
+                if (ok) x = sizeof(TIn) == 1 ? lut[(int)ip[c]] : (float)ip[c];
+                v[cx][c] = x;
             }
         }
-    }
-    uint4 *op = out + p * 4;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = pack_bf16x2(fmaxf(acc[q * 8 + 0], 0.f), fmaxf(acc[q * 8 + 1], 0.f));
-        o.y = pack_bf16x2(fmaxf(acc[q * 8 + 2], 0.f), fmaxf(acc[q * 8 + 3], 0.f));
-        o.z = pack_bf16x2(fmaxf(acc[q * 8 + 4], 0.f), fmaxf(acc[q * 8 + 5], 0.f));
-        o.w = pack_bf16x2(fmaxf(acc[q * 8 + 6], 0.f), fmaxf(acc[q * 8 + 7], 0.f));
-        op[q] = o;
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 v0 = make_float2(v[dx][c], v[dx][c]), v1 = make_float2(v[dx + 2][c], v[dx + 2][c]);
+                const float *wr = c_conv1_w + ((dy * 3 + dx) * 3 + c) * 32;
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {
+                    const float2 w2 = make_float2(wr[2 * n], wr[2 * n + 1]);
+                    acc[0][n] = ffma2(v0, w2, acc[0][n]);
+                    acc[1][n] = ffma2(v1, w2, acc[1][n]);
+                }
+            }
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+        if (px == 1 && !two) break;
+        uint4 *op = out + (((long long)b * Ho + oy) * Wo + ox + px) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(fmaxf(acc[px][q * 4 + 0].x, 0.f), fmaxf(acc[px][q * 4 + 0].y, 0.f));
+            o.y = pack_bf16x2(fmaxf(acc[px][q * 4 + 1].x, 0.f), fmaxf(acc[px][q * 4 + 1].y, 0.f));
+            o.z = pack_bf16x2(fmaxf(acc[px][q * 4 + 2].x, 0.f), fmaxf(acc[px][q * 4 + 2].y, 0.f));
+            o.w = pack_bf16x2(fmaxf(acc[px][q * 4 + 3].x, 0.f), fmaxf(acc[px][q * 4 + 3].y, 0.f));
+            op[q] = o;
+        }
     }
 }
 
 cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s) {
     SamePad ph = same_pad(H, 3, 2, 1), pw = same_pad(W, 3, 2, 1);
-    long long total = (long long)B * ph.out * pw.out;
+    long long total = (long long)B * ph.out * ((pw.out + 1) / 2);      // one thread per pair of output pixels
     unsigned grid = (unsigned)((total + 127) / 128);
     if (in_is_u8)
         return launch_chain(conv1_bf16_kernel<uint8_t>, grid, 128, 0, s, 1, (const uint8_t *)in, (uint4 *)out, B, H, W, ph.out,
