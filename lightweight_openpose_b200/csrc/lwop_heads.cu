@@ -32,8 +32,8 @@ namespace {
 
 constexpr int kHpThreads = 384;
 constexpr int kHpEpiWarp0 = 4;
-constexpr int kW1Stages = 8;                  // [128 x 64] bf16 chunks, 16 KB each
-constexpr int kW2Stages = 2;                  // [<=32 x 128] bf16 slices as two 4 KB K-chunks
+constexpr int kW1Stages = 6;                  // [128 x 64] bf16 chunks, 16 KB each
+constexpr int kW2Stages = 4;                  // [<=32 x 128] bf16 slices as two 4 KB K-chunks
 constexpr int kXStages = 2;                   // [128 x 128] bf16 input tiles, 32 KB each
 
 struct HpSmem {
@@ -44,7 +44,7 @@ struct HpSmem {
     static constexpr int kW1Off = kXOff + kXStages * kXBytes;
     static constexpr int kW2Off = kW1Off + kW1Stages * kW1Bytes;
     static constexpr int kBarOff = kW2Off + kW2Stages * kW2Bytes;
-    static constexpr int kNumBars = 2 * kXStages + 2 * kW1Stages + 2 * kW2Stages + 4 + 4 + 2;
+    static constexpr int kNumBars = 2 * kXStages + 2 * kW1Stages + 2 * kW2Stages + 4 + 4 + 4;
     static constexpr int kBias1Off = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
     static constexpr int kBias2Off = kBias1Off + 1024 * 4;
     static constexpr int kTotal = kBias2Off + 64 * 4;
@@ -78,8 +78,10 @@ enum { HP_TOTAL = 0, HP_MMA_X, HP_MMA_ACC1_EMPTY, HP_MMA_W1, HP_MMA_A2_FULL, HP_
         }                                                             \
     } while (0)
 
-constexpr uint32_t kAcc2ColA = 256, kAcc2ColB = 288;
-constexpr uint32_t kA2TmemCol = 320;           // two 64-column buffers: bf16 hidden activations as the TMEM A operand of MMA2
+// TMEM columns: acc1 stages [0,256); two acc2 stages of 64 columns ([+0,+16) heat, [+32,+64) paf) at 256 / 320;
+// two 64-column A2 buffers (bf16 hidden activations, the TMEM A operand of MMA2) at 384 / 448
+constexpr uint32_t kAcc2Col = 256, kAcc2Stride = 64, kAcc2OffB = 32;
+constexpr uint32_t kA2TmemCol = 384;
 
 __global__ void __launch_bounds__(kHpThreads, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1a,
@@ -102,9 +104,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint64_t *acc1_empty = acc1_full + 2;            // [2]
     uint64_t *a2_full = acc1_empty + 2;              // [2]
     uint64_t *a2_empty = a2_full + 2;                // [2]
-    uint64_t *acc2_full = a2_empty + 2;
-    uint64_t *acc2_empty = acc2_full + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc2_empty + 1);
+    uint64_t *acc2_full = a2_empty + 2;              // [2]
+    uint64_t *acc2_empty = acc2_full + 2;            // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc2_empty + 2);
     float *bias1_s = reinterpret_cast<float *>(smem + L::kBias1Off);
     float *bias2_s = reinterpret_cast<float *>(smem + L::kBias2Off);
 
@@ -132,8 +134,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_init(&a2_full[i], 4);
             mbar_init(&a2_empty[i], 1);
         }
-        mbar_init(acc2_full, 1);
-        mbar_init(acc2_empty, 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc2_full[i], 1);
+            mbar_init(&acc2_empty[i], 4);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_ptr);
@@ -147,16 +151,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
     if (warp == 0) {
-        // ===================== TMA producer: input tiles + first-layer weight chunks =====================
+        // ===================== TMA producer: first-layer weight chunks (one stream across all tiles) =====================
         if (lane == 0) {
-            int xs = 0, ws = 0;
-            uint32_t xph = 0, wph = 0;
+            int ws = 0;
+            uint32_t wph = 0;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-                mbar_wait_sel(&x_empty[xs], xph ^ 1, p.park & 1u);
-                mbar_arrive_expect_tx(&x_full[xs], L::kXBytes);
-                tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
-                tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
-                if (++xs == kXStages) { xs = 0; xph ^= 1; }
                 for (int pp = 0; pp < P; ++pp) {
                     const CUtensorMap *mw = pp < half ? &map_w1a : &map_w1b;
                     const int row0 = (pp < half ? pp : pp - half) * 128;
@@ -167,6 +166,19 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         if (++ws == kW1Stages) { ws = 0; wph ^= 1; }
                     }
                 }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA producer: input tiles (its own warp: an X stage wait must not hold back weights) =====================
+        if (lane == 0) {
+            int xs = 0;
+            uint32_t xph = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                mbar_wait_sel(&x_empty[xs], xph ^ 1, p.park & 1u);
+                mbar_arrive_expect_tx(&x_full[xs], L::kXBytes);
+                tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
+                tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
+                if (++xs == kXStages) { xs = 0; xph ^= 1; }
             }
         }
     } else if (warp == 3) {
@@ -198,16 +210,19 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         uint32_t xph = 0, w1ph = 0, w2ph = 0;
         uint32_t use0 = 0, use1 = 0;       // uses of acc1 stage 0 / 1 (MMA1), phase bookkeeping
         uint32_t useb0 = 0, useb1 = 0;     // uses of A2 buffer 0 / 1 (MMA2)
-        int local_tile = 0;
-        auto mma2 = [&](int pp) {
-            const int buf = pp & 1;
+        // MMA2 runs TWO passes behind MMA1 in one flat schedule over all tiles of this CTA: when MMA2(m) is issued the
+        // epilogue of pass m finished a whole pass ago, so the MMA thread does not sit on the epilogue's latency and the
+        // tensor pipe keeps working on MMA1(m + 1), MMA1(m + 2) meanwhile.  acc2 is double-buffered for the same reason.
+        int m2_tile = 0, m2_pp = 0;        // (local tile, pass) of the next MMA2
+        auto mma2 = [&]() {
+            const int pp = m2_pp, buf = pp & 1, st = m2_tile & 1;
             HP_WAIT(HP_MMA_A2_FULL, mbar_wait_sel(&a2_full[buf], (buf ? useb1 : useb0) & 1, p.park & 2u));
-            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(acc2_empty, (uint32_t)((local_tile & 1) ^ 1), p.park & 2u));
+            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(&acc2_empty[st], (uint32_t)(((m2_tile >> 1) & 1) ^ 1), p.park & 2u));
             HP_WAIT(HP_MMA_W2, mbar_wait_sel(&w2_full[w2s], w2ph, p.park & 2u));
             tcgen05_fence_after();
             const bool is_a = pp < half;
             const int kslice = is_a ? pp : pp - half;
-            const uint32_t d = tmem_base + (is_a ? kAcc2ColA : kAcc2ColB);
+            const uint32_t d = tmem_base + kAcc2Col + (uint32_t)st * kAcc2Stride + (is_a ? 0u : kAcc2OffB);
             const uint32_t w2 = smem_u32(smem + L::kW2Off + w2s * L::kW2Bytes);
             if (elect_one()) {
                 // A operand = the hidden activations the epilogue wrote back to tensor memory (no shared-memory round trip)
@@ -222,11 +237,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
                 umma_commit(&a2_empty[buf]);
                 umma_commit(&w2_empty[w2s]);
+                if (pp == P - 1) umma_commit(&acc2_full[st]);
             }
             __syncwarp();
             if (buf) ++useb1; else ++useb0;
             if (++w2s == kW2Stages) { w2s = 0; w2ph ^= 1; }
+            if (++m2_pp == P) { m2_pp = 0; ++m2_tile; }
         };
+        int issued1 = 0;                   // MMA1 passes issued so far
+        int local_tile = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
             HP_WAIT(HP_MMA_X, mbar_wait_sel(&x_full[xs], xph, p.park & 2u));
             const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
@@ -255,25 +274,63 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     if (++w1s == kW1Stages) { w1s = 0; w1ph ^= 1; }
                 }
                 if (s) ++use1; else ++use0;
-                if (pp >= 1) mma2(pp - 1);
+                if (++issued1 >= 3) mma2();
             }
-            mma2(P - 1);
-            if (elect_one()) umma_commit(acc2_full);
-            __syncwarp();
             if (++xs == kXStages) { xs = 0; xph ^= 1; }
         }
+        while (m2_tile < local_tile) mma2();     // the two (or fewer) passes still in flight
     } else if (warp >= kHpEpiWarp0) {
         // ===================== epilogue groups =====================
         const int q = (warp - kHpEpiWarp0) & 3;               // TMEM lane quarter == warp % 4
         const int grp = (warp - kHpEpiWarp0) >> 2;            // owns acc1 stage / A2 buffer `grp`
         const int row = q * 32 + lane;                        // row of the tile == TMEM lane
         uint32_t use = 0;
-        int local_tile = 0;
+        // ---- epilogue-2: the two narrow linear outputs of a tile (group 0; acc2 stage = local tile & 1) ----
+        auto epilogue2 = [&](int lt, int tile) {
+            const int st = lt & 1;
+            HP_WAIT(HP_E_ACC2_FULL, mbar_wait_sel(&acc2_full[st], (uint32_t)((lt >> 1) & 1), p.park & 8u));
+            const long long hp_e2 = p.prof ? clock64() : 0;
+            tcgen05_fence_after();
+            uint32_t ra[16], rb[32];
+            const uint32_t t2 = tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2Col + (uint32_t)st * kAcc2Stride;
+            tmem_ld_32x32b_x16(t2, ra);
+            tmem_ld_32x32b_x32(t2 + kAcc2OffB, rb);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc2_empty[st]);
+            const long long m = (long long)tile * 128 + row;
+            if (m < p.M) {
+                float va[14], vb[26];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) va[j] = __uint_as_float(ra[j]) + bias2_s[j];
+#pragma unroll
+                for (int j = 0; j < 26; ++j) vb[j] = __uint_as_float(rb[j]) + bias2_s[16 + j];
+                if (p.out_a) {
+                    float2 *o = reinterpret_cast<float2 *>(p.out_a + m * 14);     // 56-byte rows: 8-byte aligned
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) o[j] = make_float2(va[2 * j], va[2 * j + 1]);
+                }
+                if (p.out_b) {
+                    float2 *o = reinterpret_cast<float2 *>(p.out_b + m * 26);     // 104-byte rows
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) o[j] = make_float2(vb[2 * j], vb[2 * j + 1]);
+                }
+                if (p.cat) {
+                    __nv_bfloat16 *o = p.cat + m * p.ldc;
+#pragma unroll
+                    for (int j = 0; j < 14; ++j) o[p.cat_col_a + j] = __float2bfloat16_rn(va[j]);
+#pragma unroll
+                    for (int j = 0; j < 26; ++j) o[p.cat_col_b + j] = __float2bfloat16_rn(vb[j]);
+                }
+            }
+            if (p.prof) hp_acc[HP_E2_WORK] += (unsigned long long)(clock64() - hp_e2);
+        };
+        int local_tile = 0, prev_tile = -1;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
             for (int pp = grp; pp < P; pp += 2, ++use) {
                 HP_WAIT(HP_E_ACC1_FULL, mbar_wait_sel(&acc1_full[grp], use & 1, p.park & 8u));
                 tcgen05_fence_after();
-                HP_WAIT(HP_E_A2_EMPTY, mbar_wait_sel(&a2_empty[grp], (use & 1) ^ 1, p.park & 8u));   // MMA2 that read this buffer two passes ago retired
                 const long long hp_e0 = p.prof ? clock64() : 0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
                 const float *b1 = bias1_s + pp * 128;
@@ -300,10 +357,14 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                                 make_float2(bq.x, bq.y));
                         const float2 s3 = fadd2(make_float2(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7])),
                                                 make_float2(bq.z, bq.w));
-                        uint4 o;
-                        o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
-                        o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
-                        pk[j * 4 + 0] = o.x; pk[j * 4 + 1] = o.y; pk[j * 4 + 2] = o.z; pk[j * 4 + 3] = o.w;
+                        pk[j * 4 + 0] = pack_relu_bf16x2(s0.x, s0.y); pk[j * 4 + 1] = pack_relu_bf16x2(s1.x, s1.y);
+                        pk[j * 4 + 2] = pack_relu_bf16x2(s2.x, s2.y); pk[j * 4 + 3] = pack_relu_bf16x2(s3.x, s3.y);
+                    }
+                    if (c == 0) {
+                        // the MMA2 that read this A2 buffer two passes ago has retired (it was issued right behind this
+                        // pass's MMA1, so the wait sits after the first load + math rather than in front of them)
+                        HP_WAIT(HP_E_A2_EMPTY, mbar_wait_sel(&a2_empty[grp], (use & 1) ^ 1, p.park & 8u));
+                        tcgen05_fence_after();
                     }
                     // TMEM A operand of MMA2: lane = row, hidden column k of this pass in 32-bit column k / 2
                     tmem_st_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kA2TmemCol + (uint32_t)(grp * 64 + c * 16), pk);
@@ -313,47 +374,13 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 __syncwarp();                                  // orders the lanes' stores before lane 0's release
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if (p.prof) hp_acc[HP_E1_WORK] += (unsigned long long)(clock64() - hp_e0);
+                // the previous tile's outputs: its last MMA2 is issued two passes into this tile, so group 0 drains
+                // acc2 after its first pass here instead of stalling the new tile's accumulator stage
+                if (grp == 0 && pp == 0 && prev_tile >= 0) epilogue2(local_tile - 1, prev_tile);
             }
-            if (grp == 0) {
-                // ---- epilogue-2: the two narrow linear outputs of this tile ----
-                HP_WAIT(HP_E_ACC2_FULL, mbar_wait_sel(acc2_full, (uint32_t)(local_tile & 1), p.park & 8u));
-                const long long hp_e2 = p.prof ? clock64() : 0;
-                tcgen05_fence_after();
-                uint32_t ra[16], rb[32];
-                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2ColA, ra);
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2ColB, rb);
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc2_empty);
-                const long long m = (long long)tile * 128 + row;
-                if (m < p.M) {
-                    float va[14], vb[26];
-#pragma unroll
-                    for (int j = 0; j < 14; ++j) va[j] = __uint_as_float(ra[j]) + bias2_s[j];
-#pragma unroll
-                    for (int j = 0; j < 26; ++j) vb[j] = __uint_as_float(rb[j]) + bias2_s[16 + j];
-                    if (p.out_a) {
-                        float2 *o = reinterpret_cast<float2 *>(p.out_a + m * 14);     // 56-byte rows: 8-byte aligned
-#pragma unroll
-                        for (int j = 0; j < 7; ++j) o[j] = make_float2(va[2 * j], va[2 * j + 1]);
-                    }
-                    if (p.out_b) {
-                        float2 *o = reinterpret_cast<float2 *>(p.out_b + m * 26);     // 104-byte rows
-#pragma unroll
-                        for (int j = 0; j < 13; ++j) o[j] = make_float2(vb[2 * j], vb[2 * j + 1]);
-                    }
-                    if (p.cat) {
-                        __nv_bfloat16 *o = p.cat + m * p.ldc;
-#pragma unroll
-                        for (int j = 0; j < 14; ++j) o[p.cat_col_a + j] = __float2bfloat16_rn(va[j]);
-#pragma unroll
-                        for (int j = 0; j < 26; ++j) o[p.cat_col_b + j] = __float2bfloat16_rn(vb[j]);
-                    }
-                }
-                if (p.prof) hp_acc[HP_E2_WORK] += (unsigned long long)(clock64() - hp_e2);
-            }
+            prev_tile = tile;
         }
+        if (grp == 0 && prev_tile >= 0) epilogue2(local_tile - 1, prev_tile);
     }
     if (p.prof && lane == 0 && (warp == 1 || warp == kHpEpiWarp0)) {
         if (warp == 1) hp_acc[HP_TOTAL] = (unsigned long long)(clock64() - hp_start);
