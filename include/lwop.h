@@ -144,6 +144,8 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
  * Joint ids are the running counter over (channel, peak) that NMS assigns (pose_decode.py:135,182-183). */
 #define LWOP_PEAKS_NO_REFINE 1   /* NMS(bool_refine_center=False): low-res peak snapped to the up-scaled grid (:176-182) */
 #define LWOP_PEAKS_CROSS     2   /* peak search = find_peaks (:37-49, 3x3 cross maximum filter) instead of find_peaks_v2 */
+#define LWOP_PEAKS_GAUSS     4   /* NMS(bool_gaussian_filt=True): scipy gaussian_filter(sigma=3) of the up-sampled patch before
+                                    the argmax (:163-164); needs 5 * factor <= 48 */
 
 /* NMS (pose_decode.py:107-185): heat_dev [batch][h][w][14] float32, `factor` = upsampFactor.  Also zeroes
  * counts_dev [batch][LWOP_COUNTS] and sets its overflow bit (counts[b][2] & 1) if a channel has more than

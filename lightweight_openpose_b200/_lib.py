@@ -24,7 +24,7 @@ DT_F32, DT_BF16 = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_NO_FUSE_SEP = 2
 FLAG_NO_FUSE_HEADS = 4
-PEAKS_NO_REFINE, PEAKS_CROSS = 1, 2
+PEAKS_NO_REFINE, PEAKS_CROSS, PEAKS_GAUSS = 1, 2, 4
 NUM_JOINTS, NUM_PAFS, NUM_LIMBS = 14, 26, 13
 MAX_PEAKS, MAX_JOINTS, MAX_PERSONS, COUNTS = 128, 1792, 128, 32
 

@@ -80,6 +80,33 @@ __device__ __forceinline__ int cv_round(double v) { return (int)rint(v); }
 // ---------------------------------------------------------------------------
 constexpr int kRefineMax = 48;      // separable refinement handles up-sampled patches up to 48 x 48 (5 x 8 = 40 here)
 
+// NMS(bool_gaussian_filt=True) (:163-164): scipy.ndimage.gaussian_filter(patch, sigma=3).  truncate 4.0 -> radius 12.
+// Weights at offsets -12..0 as scipy computes them in float64 (exp(-0.5 / 9 * x^2) / sum; symmetric); generated with
+// numpy, checked by tests/test_oracle_decode.py against oracle.decode_oracle.gaussian_weights().
+constexpr int kGaussRadius = 12;
+__constant__ double c_gauss3[kGaussRadius + 1] = {
+    0x1.763a210dfb306p-15, 0x1.4fbe39149e277p-13, 0x1.0d8a5ad43c165p-11, 0x1.8345966f69518p-10, 0x1.f1e9915139406p-9,
+    0x1.1e6bccad344bap-7,  0x1.26defcaeb0202p-6,  0x1.0fa58939b528fp-5,  0x1.bfde9c12bec92p-5,  0x1.4a614d1afd337p-4,
+    0x1.b42a57d56c0bep-4,  0x1.01a25f86eb137p-3,  0x1.105a329f98197p-3};
+// scipy 'reflect' border (d c b a | a b c d | d c b a), any distance
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+// one output of scipy's NI_Correlate1D, symmetric-kernel form: float64 accumulation, outermost pair first
+template <typename F>
+__device__ __forceinline__ float gauss_line(F &&at, int l, int n) {
+    double tmp = __dmul_rn((double)at(l), c_gauss3[kGaussRadius]);
+#pragma unroll 1
+    for (int j = -kGaussRadius; j < 0; ++j) {
+        const double pair = __dadd_rn((double)at(reflect_index(l + j, n)), (double)at(reflect_index(l - j, n)));
+        tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss3[j + kGaussRadius]));
+    }
+    return (float)tmp;
+}
+
 __global__ void __launch_bounds__(256)
 peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, double factor, int mode,
              float *__restrict__ peaks, int *__restrict__ peak_counts, int *__restrict__ counts) {
@@ -227,6 +254,102 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
             o[1] = (float)floor(__dsub_rn(__dmul_rn(__dadd_rn((double)py, 0.5), factor), 0.5));
             o[2] = val[p];
             o[3] = 0.0f;
+        }
+        return;
+    }
+    if (mode & LWOP_PEAKS_GAUSS) {
+        // bool_gaussian_filt=True: the up-sampled patch is smoothed (axis 0, then axis 1, each pass rounded to float32)
+        // before the argmax.  The whole block works on one peak at a time; the two patch buffers sit behind the
+        // channel map in dynamic shared memory (the host sizes it for this mode and checks the patch fits).
+        float *gu = reinterpret_cast<float *>(cand + npix) + 4;
+        float *gt = gu + kRefineMax * kRefineMax;
+        __shared__ float s_rv[8];
+        __shared__ int s_ri[8];
+        for (int i = 0; i < n; ++i) {
+            const int p = s_kept[i];
+            const int py = p / w, px = p - py * w;
+            const int x0 = max(0, px - kPatchHalf), y0 = max(0, py - kPatchHalf);
+            const int x1 = min(w - 1, px + kPatchHalf), y1 = min(h - 1, py + kPatchHalf);
+            const int pw = x1 - x0 + 1, ph = y1 - y0 + 1;
+            const int dw = cv_round((double)pw * factor), dh = cv_round((double)ph * factor);
+            for (int d = tid; d < dw; d += blockDim.x) {
+                int sx;
+                float fx, c[4];
+                src_pos(d, scale, sx, fx);
+                cubic_coeffs(fx, c);
+                s_sx[0][d] = (signed char)sx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_cx[0][d][k] = c[k];
+            }
+            for (int d = tid; d < dh; d += blockDim.x) {
+                int sy;
+                float fy, c[4];
+                src_pos(d, scale, sy, fy);
+                cubic_coeffs(fy, c);
+                s_sy[0][d] = (signed char)sy;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_cy[0][d][k] = c[k];
+            }
+            __syncthreads();
+            for (int e = tid; e < ph * dw; e += blockDim.x) {            // horizontal bicubic pass
+                const int r = e / dw, ox = e - r * dw;
+                const int sx = s_sx[0][ox];
+                float t[4], c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    t[k] = val[(y0 + r) * w + x0 + clampi(sx - 1 + k, 0, pw - 1)];
+                    c[k] = s_cx[0][ox][k];
+                }
+                s_h[0][r][ox] = dot4(t, c);
+            }
+            __syncthreads();
+            for (int d = tid; d < dw * dh; d += blockDim.x) {            // vertical bicubic pass -> gu
+                const int oy = d / dw, ox = d - oy * dw;
+                const int sy = s_sy[0][oy];
+                float t[4], c[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    t[r] = s_h[0][clampi(sy - 1 + r, 0, ph - 1)][ox];
+                    c[r] = s_cy[0][oy][r];
+                }
+                gu[d] = dot4_rev(t, c);
+            }
+            __syncthreads();
+            for (int d = tid; d < dw * dh; d += blockDim.x) {            // gaussian along axis 0 (rows) -> gt
+                const int oy = d / dw, ox = d - oy * dw;
+                gt[d] = gauss_line([&](int y) { return gu[y * dw + ox]; }, oy, dh);
+            }
+            __syncthreads();
+            float best_v = -INFINITY;
+            int best_i = 0x7fffffff;
+            for (int d = tid; d < dw * dh; d += blockDim.x) {            // gaussian along axis 1 (columns) + argmax
+                const int oy = d / dw, ox = d - oy * dw;
+                const float v = gauss_line([&](int x) { return gt[oy * dw + x]; }, ox, dw);
+                if (v > best_v) { best_v = v; best_i = d; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+            }
+            if (lane == 0) { s_rv[warp] = best_v; s_ri[warp] = best_i; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = 1; k < nwarps; ++k)
+                    if (s_rv[k] > best_v || (s_rv[k] == best_v && s_ri[k] < best_i)) { best_v = s_rv[k]; best_i = s_ri[k]; }
+                const int my = best_i / dw, mx = best_i - my * dw;
+                const double cxp = __dsub_rn(__dmul_rn(__dadd_rn((double)(px - x0), 0.5), factor), 0.5);
+                const double cyp = __dsub_rn(__dmul_rn(__dadd_rn((double)(py - y0), 0.5), factor), 0.5);
+                const double ax = __dsub_rn(__dmul_rn(__dadd_rn((double)px, 0.5), factor), 0.5);
+                const double ay = __dsub_rn(__dmul_rn(__dadd_rn((double)py, 0.5), factor), 0.5);
+                float *o = peaks + (((long long)b * LWOP_NUM_JOINTS + ch) * LWOP_MAX_PEAKS + i) * 4;
+                o[0] = (float)floor(__dadd_rn(ax, __dsub_rn((double)mx, cxp)));
+                o[1] = (float)floor(__dadd_rn(ay, __dsub_rn((double)my, cyp)));
+                o[2] = best_v;
+                o[3] = 0.0f;
+            }
+            __syncthreads();
         }
         return;
     }
@@ -833,7 +956,12 @@ cudaError_t launch_decode_peaks(const float *heat, int B, int h, int w, double f
                                 float *peaks, int *peak_counts, int *counts, cudaStream_t s) {
     const int npix = h * w;
     if (npix > kMaxPixPerThread * 256) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)npix * 8 + 16;
+    size_t smem = (size_t)npix * 8 + 16;
+    if (mode & LWOP_PEAKS_GAUSS) {
+        // the smoothed patch lives in shared memory: the clipped 5x5 patch times `factor` must fit 48 x 48
+        if ((int)rint(5.0 * factor) > kRefineMax) return cudaErrorInvalidValue;
+        smem += 2 * (size_t)kRefineMax * kRefineMax * sizeof(float) + 16;
+    }
     if (smem > 160 * 1024) return cudaErrorInvalidValue;
     if (smem > 16 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

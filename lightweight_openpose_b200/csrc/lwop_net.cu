@@ -895,7 +895,11 @@ int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int ma
     if (!h || !heat_dev || !peaks_dev || !peak_counts_dev || !counts_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
     if (batch < 1 || map_h < 1 || map_w < 1 || !(factor > 0.0)) return fail(h, LWOP_ERR_INVALID, "bad geometry");
     if ((long long)map_h * map_w > 16384) return fail(h, LWOP_ERR_UNSUPPORTED, "heat map larger than 16384 pixels");
-    if (mode & ~(LWOP_PEAKS_NO_REFINE | LWOP_PEAKS_CROSS)) return fail(h, LWOP_ERR_INVALID, "unknown peak mode");
+    if (mode & ~(LWOP_PEAKS_NO_REFINE | LWOP_PEAKS_CROSS | LWOP_PEAKS_GAUSS)) return fail(h, LWOP_ERR_INVALID, "unknown peak mode");
+    if ((mode & LWOP_PEAKS_GAUSS) && (mode & LWOP_PEAKS_NO_REFINE))
+        return fail(h, LWOP_ERR_INVALID, "the Gaussian filter applies to the refined patch only");
+    if ((mode & LWOP_PEAKS_GAUSS) && 5.0 * factor > 48.4)
+        return fail(h, LWOP_ERR_UNSUPPORTED, "Gaussian patch filter needs upsampFactor <= 9.6 (patch <= 48 x 48)");
     CU_OK(h, cudaSetDevice(h->device));
     CU_OK(h, launch_decode_peaks(heat_dev, batch, map_h, map_w, factor, thre1, mode, peaks_dev, peak_counts_dev,
                                  counts_dev, (cudaStream_t)stream));

@@ -144,17 +144,17 @@ def NMS(param, heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian
     """Per joint type an ``(n, 5)`` float64 array ``(x, y, score, id, 0)`` (reference :107-185), computed by
     the CUDA peak kernel: greedy radius-5 search of ``find_peaks_v2`` (:146) and, with ``bool_refine_center``,
     the bicubic refinement of the clipped 5x5 patch (:149-175); without it the low-res peak snapped to the
-    up-scaled grid (:176-182).  The optional Gaussian smoothing of the patch (:163-164, off in every reference
-    caller) is not implemented."""
-    if bool_gaussian_filt:
-        raise NotImplementedError("bool_gaussian_filt=True (scipy gaussian_filter on the up-sampled patch) is not on "
-                                  "the GPU path; the reference never enables it")
+    up-scaled grid (:176-182).  ``bool_gaussian_filt`` smooths the up-sampled patch with scipy's
+    ``gaussian_filter(sigma=3)`` arithmetic before the argmax (:163-164); like the reference it only has an effect
+    together with ``bool_refine_center``."""
     heat = _heat_to_dev(heatmaps)
     if heat.dim() != 3 or heat.shape[-1] != NUM_JOINTS:
         raise ValueError("heatmaps must be [h, w, 14]")
     h, w = int(heat.shape[0]), int(heat.shape[1])
     e = _decode_engine(max(16, h), max(16, w), 1)
     mode = 0 if bool_refine_center else _lib.PEAKS_NO_REFINE
+    if bool_gaussian_filt and bool_refine_center:
+        mode |= _lib.PEAKS_GAUSS
     peaks, pc, counts = e.nms_device(heat[None], float(upsampFactor), float(param['thre1']), mode)
     _check_overflow(counts.cpu().numpy())
     return _peak_lists(peaks, pc)

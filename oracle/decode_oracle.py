@@ -173,11 +173,52 @@ def cross_peaks(channel: np.ndarray, thre1: float) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # D2: patch refinement -- pose_decode.py:107-185 (NMS) + :80-104
 # ----------------------------------------------------------------------------
+GAUSS_SIGMA = 3.0                                  # NMS passes sigma=3 (:163-164)
+GAUSS_RADIUS = int(4.0 * GAUSS_SIGMA + 0.5)        # scipy: truncate = 4.0 -> 12
+
+
+def gaussian_weights(sigma: float = GAUSS_SIGMA, radius: int = GAUSS_RADIUS) -> np.ndarray:
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0): float64 weights at offsets -radius..radius."""
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def _reflect_index(i: int, n: int) -> int:
+    """scipy 'reflect' border (half-sample symmetric: d c b a | a b c d | d c b a), any distance."""
+    period = 2 * n
+    i %= period
+    return i if i < n else period - 1 - i
+
+
+def gaussian_filter_f32(img: np.ndarray, sigma: float = GAUSS_SIGMA) -> np.ndarray:
+    """``scipy.ndimage.gaussian_filter(img, sigma)`` for a float32 2-D array, restated from scipy's
+    NI_Correlate1D (third-party, scipy >= 1.0; the reference imports it at pose_decode.py:8): axis 0 then axis 1,
+    each line extended by reflection, float64 accumulation in the symmetric-kernel order
+    ``tmp = x[l] * w[0]; for j = -r..-1: tmp += (x[l + j] + x[l - j]) * w[j]``, every pass rounded to float32."""
+    radius = int(4.0 * sigma + 0.5)
+    w = gaussian_weights(sigma, radius)
+    out = np.asarray(img, dtype=np.float32)
+    for axis in (0, 1):
+        src = out if axis == 1 else out.T                       # lines along `axis` as rows
+        n = src.shape[1]
+        idx = np.array([_reflect_index(i, n) for i in range(-radius, n + radius)])
+        ext = src[:, idx].astype(np.float64)                     # [lines, n + 2r]
+        centre = np.arange(n) + radius
+        tmp = ext[:, centre] * w[radius]
+        for j in range(-radius, 0):
+            tmp = tmp + (ext[:, centre + j] + ext[:, centre - j]) * w[j + radius]
+        res = tmp.astype(np.float32)
+        out = res if axis == 1 else res.T
+    return np.ascontiguousarray(out)
+
+
 def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: bool = True,
-                 refine: bool = True) -> List[np.ndarray]:
+                 refine: bool = True, gaussian: bool = False) -> List[np.ndarray]:
     """Per joint type an array [n, 5] float64 of ``(x, y, score, id, 0)`` at
     input-image resolution; ``id`` counts peaks over channels then peaks.
-    ``refine=False`` is ``NMS(bool_refine_center=False)`` (:176-182)."""
+    ``refine=False`` is ``NMS(bool_refine_center=False)`` (:176-182); ``gaussian=True`` is
+    ``NMS(bool_gaussian_filt=True)`` (:163-164): the up-sampled patch is smoothed before the argmax."""
     h, w = heatmaps.shape[:2]
     per_type: List[np.ndarray] = []
     next_id = 0
@@ -194,6 +235,8 @@ def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: boo
             x0, y0 = max(0, px - PATCH_HALF), max(0, py - PATCH_HALF)          # (:150)
             x1, y1 = min(w - 1, px + PATCH_HALF), min(h - 1, py + PATCH_HALF)  # (:151-152)
             up = _resize_patch(ch[y0:y1 + 1, x0:x1 + 1], factor, use_cv2)      # (:156-158)
+            if gaussian:
+                up = gaussian_filter_f32(up)                                   # (:163-164)
             flat = int(np.argmax(up))                                          # first max, row-major (:167)
             my, mx = divmod(flat, up.shape[1])
             # (:171-182) floor(resized(peak) + (argmax - resized(peak - patch_origin)))

@@ -40,6 +40,7 @@ def _load_golden(fname):
             "joint_list": z[f"{name}/joint_list"],
             "limbs": [z[f"{name}/limb{t}"] for t in range(13)],
             "persons": z[f"{name}/persons"], "joints": z[f"{name}/joints"],
+            "nms_gauss": z[f"{name}/nms_gauss"],
         }
     return scenes, {"thre1": float(z["thre"][0]), "thre2": float(z["thre"][1])}
 

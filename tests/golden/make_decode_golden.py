@@ -82,6 +82,10 @@ def main(use_ipp=True, fname="decode_golden.npz"):
             out[f"{name}/limb{t}"] = np.asarray(limbs[t], dtype=np.float64).reshape(-1, 5)
         out[f"{name}/persons"] = np.asarray(persons_arr, dtype=np.float64)
         out[f"{name}/joints"] = np.asarray(joints, dtype=np.float32)
+        # alternate mode of SURVEY 8(f) row 4: NMS with the Gaussian-smoothed patch (:163-164), rows (x, y, score, id, 0, type)
+        gauss = ref.NMS(param, heat, scale, True, True)
+        out[f"{name}/nms_gauss"] = np.array([tuple(pk) + (jt,) for jt, pks in enumerate(gauss) for pk in pks],
+                                            dtype=np.float64).reshape(-1, 6)
         print(name, "joints", len(joint_list), "persons", persons_arr.shape, "conns",
               sum(len(l) for l in limbs))
     out["names"] = np.array(names)

@@ -171,3 +171,21 @@ def test_decode_stage_functions_match_oracle(spec):
         assert np.array_equal(got_p[:, :14], want_p[:, :14]) and np.array_equal(got_p[:, 15], want_p[:, 15])
         assert np.abs(got_p[:, 14] - want_p[:, 14]).max() <= 1e-9
         assert got_p.shape[0] == persons
+
+
+def test_nms_gaussian_patch_filter(decode_golden_noipp):
+    """NMS(bool_gaussian_filt=True) (pose_decode.py:163-164) on the GPU: bit-exact against the reference module's own
+    output (OpenCV's own bicubic + scipy's gaussian_filter) and against the oracle on fresh scenes."""
+    scenes, param = decode_golden_noipp
+    for name, sc in scenes.items():
+        factor = sc["hw"][0] / sc["heat"].shape[0]
+        got = pose_decode.NMS(param, sc["heat"], factor, True, True)
+        rows = np.array([tuple(pk) + (jt,) for jt, pks in enumerate(got) for pk in pks], dtype=np.float64).reshape(-1, 6)
+        assert rows.shape == sc["nms_gauss"].shape and np.array_equal(rows, sc["nms_gauss"]), name
+    for seed, persons, H, W in ((510, 5, 368, 368), (511, 14, 368, 656)):
+        heat, _, _ = synth.synth_scene(seed, persons, H, W, noise=0.05)
+        got = pose_decode.NMS(PARAM, heat, 8.0, bool_gaussian_filt=True)
+        want = orc.refine_peaks(heat, PARAM["thre1"], 8.0, use_cv2=False, gaussian=True)
+        _lists_equal(got, want, tol=0.0)
+        # without centre refinement the flag has no effect, as in the reference
+        _lists_equal(pose_decode.NMS(PARAM, heat, 8.0, False, True), orc.refine_peaks(heat, PARAM["thre1"], 8.0, refine=False), tol=0.0)

@@ -142,3 +142,47 @@ def test_restatement_is_bit_exact_vs_reference_without_ipp(decode_golden_noipp):
     for name, sc in scenes.items():
         got = orc.decode_detail(sc["hw"], param, sc["heat"], sc["paf"], use_cv2=False)
         compare_decode(got, sc, float_tol=0.0, f64_tol=1e-14)
+
+
+def test_gaussian_filter_restatement_equals_scipy():
+    """NMS(bool_gaussian_filt=True) smooths the up-sampled patch with scipy.ndimage.gaussian_filter(sigma=3)
+    (pose_decode.py:8,163-164; third-party, scipy as installed): the numpy restatement is bit-identical, also for
+    lines shorter than the 12-sample kernel radius (multiple reflections)."""
+    scipy_ndimage = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(11)
+    for shape in [(40, 40), (24, 40), (40, 24), (24, 24), (8, 8), (5, 17), (48, 48)]:
+        for _ in range(5):
+            a = rng.normal(0.3, 0.2, size=shape).astype(np.float32)
+            want = scipy_ndimage.gaussian_filter(a, sigma=3)
+            got = orc.gaussian_filter_f32(a)
+            assert want.dtype == got.dtype == np.float32 and np.array_equal(want, got)
+
+
+def test_gaussian_weights_match_the_kernel_constants():
+    """The CUDA kernel carries the 13 float64 weights as hex literals; they must be numpy's."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "lightweight_openpose_b200", "csrc", "lwop_decode.cu")).read()
+    block = src[src.index("c_gauss3[kGaussRadius + 1] = {"):]
+    lits = re.findall(r"0x1\.[0-9a-f]+p-\d+", block[:block.index("};")])
+    w = orc.gaussian_weights()
+    assert len(lits) == 13 and [float.fromhex(v) for v in lits] == [float(v) for v in w[:13]]
+    assert np.array_equal(w, w[::-1])
+
+
+def test_oracle_gaussian_nms_matches_reference_golden(decode_golden_noipp, decode_golden):
+    """refine_peaks(gaussian=True) against the reference module's NMS(..., True, True): exact on OpenCV's own
+    bicubic (IPP off); on an IPP build integer fields are exact and scores agree to 1e-6."""
+    for (scenes, param), use_cv2, tol in ((decode_golden_noipp, False, 0.0), (decode_golden, True, 1e-6)):
+        for name, sc in scenes.items():
+            H = sc["hw"][0]
+            got = orc.refine_peaks(sc["heat"], param["thre1"], H / sc["heat"].shape[0], use_cv2=use_cv2, gaussian=True)
+            rows = np.array([tuple(pk) + (jt,) for jt, pks in enumerate(got) for pk in pks], dtype=np.float64).reshape(-1, 6)
+            want = sc["nms_gauss"]
+            assert rows.shape == want.shape, name
+            if rows.size:
+                if tol == 0.0:
+                    assert np.array_equal(rows, want), name
+                else:
+                    # a last-ulp difference of IPP's patch resize can move the argmax of the smoothed (flat-topped) patch by a pixel
+                    assert np.abs(rows[:, :2] - want[:, :2]).max() <= 1 and np.array_equal(rows[:, 3:], want[:, 3:]), name
+                    assert np.abs(rows[:, 2] - want[:, 2]).max() <= tol, name
