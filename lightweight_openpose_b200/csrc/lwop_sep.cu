@@ -448,10 +448,24 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             const long long pf_e0 = pf ? clock64() : 0;
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BLOCK_N);
+            // residual rows (tf.add) are fetched one 32-column group ahead so their latency hides behind the previous group
+            const uint4 *rbase = (p.residual && row_ok) ? reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + n0) : nullptr;
+            uint4 rnext[4] = {};
+            if (rbase) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rnext[j] = rbase[j];
+            }
 #pragma unroll 1
             for (int g = 0; g < BLOCK_N / 32; ++g) {
                 uint32_t r0[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 32), r0);
+                uint4 rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rr[j] = rnext[j];
+                if (rbase && g + 1 < BLOCK_N / 32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rnext[j] = rbase[(g + 1) * 4 + j];
+                }
                 tmem_ld_wait();
                 if (g == BLOCK_N / 32 - 1) {                  // accumulator drained: hand it back to the MMA warp
                     tcgen05_fence_before();
@@ -461,9 +475,6 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());   // previous store has finished reading the staging tile
                 __syncwarp();
                 const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0 + g * 32);
-                const uint4 *rp = (p.residual && row_ok)
-                                      ? reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + n0 + g * 32)
-                                      : nullptr;
                 if (p.act == LWOP_ACT_RELU && !p.residual) {
                     // conv_dw layers (folded BN + ReLU): packed bias add, then ReLU + bf16 pack in one instruction
 #pragma unroll
@@ -482,6 +493,30 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                         o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
                         *reinterpret_cast<uint4 *>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
                     }
+                } else if (p.act == LWOP_ACT_ELU) {
+                    // conv_dw_no_bn layers (bias + ELU, the last one + tf.add): packed bias add, branch-free packed ELU
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        float2 s0 = elu2_fast(fadd2(make_float2(__uint_as_float(r0[j * 8 + 0]), __uint_as_float(r0[j * 8 + 1])),
+                                                    make_float2(b0.x, b0.y)));
+                        float2 s1 = elu2_fast(fadd2(make_float2(__uint_as_float(r0[j * 8 + 2]), __uint_as_float(r0[j * 8 + 3])),
+                                                    make_float2(b0.z, b0.w)));
+                        float2 s2 = elu2_fast(fadd2(make_float2(__uint_as_float(r0[j * 8 + 4]), __uint_as_float(r0[j * 8 + 5])),
+                                                    make_float2(b1.x, b1.y)));
+                        float2 s3 = elu2_fast(fadd2(make_float2(__uint_as_float(r0[j * 8 + 6]), __uint_as_float(r0[j * 8 + 7])),
+                                                    make_float2(b1.z, b1.w)));
+                        if (rbase) {
+                            s0 = fadd2(s0, make_float2(bf16_lo(rr[j].x), bf16_hi(rr[j].x)));
+                            s1 = fadd2(s1, make_float2(bf16_lo(rr[j].y), bf16_hi(rr[j].y)));
+                            s2 = fadd2(s2, make_float2(bf16_lo(rr[j].z), bf16_hi(rr[j].z)));
+                            s3 = fadd2(s3, make_float2(bf16_lo(rr[j].w), bf16_hi(rr[j].w)));
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(s0.x, s0.y); o.y = pack_bf16x2(s1.x, s1.y);
+                        o.z = pack_bf16x2(s2.x, s2.y); o.w = pack_bf16x2(s3.x, s3.y);
+                        *reinterpret_cast<uint4 *>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+                    }
                 } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                 // 8 columns = one 16-byte chunk
@@ -490,10 +525,9 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[e] = apply_act_fast(__uint_as_float(r0[j * 8 + e]) + bb[e], p.act);
-                    if (rp) {
-                        const uint4 rr = rp[j];
-                        v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                        v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                    if (rbase) {
+                        v[0] += bf16_lo(rr[j].x); v[1] += bf16_hi(rr[j].x); v[2] += bf16_lo(rr[j].y); v[3] += bf16_hi(rr[j].y);
+                        v[4] += bf16_lo(rr[j].z); v[5] += bf16_hi(rr[j].z); v[6] += bf16_lo(rr[j].w); v[7] += bf16_hi(rr[j].w);
                     }
                     uint4 o;
                     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
