@@ -55,6 +55,7 @@ struct SepParams {
     int act, ldr, out_col0;
     unsigned long long *prof;       // optional [16] stall counters (LWOP_SEP_PROF=1), nullptr otherwise
     unsigned park;                  // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 2 depthwise, 3 epilogue)
+    int wide64;                     // Cout_pad == 64: one 64-column staging tile + TMA store per warp and tile (LWOP_SEP_WIDE64=0: two 32-column ones)
 };
 
 // stall accounting (debugging aid): cycles one elected thread of each role spends in each barrier wait
@@ -84,8 +85,10 @@ struct SepSmem {
     static constexpr int kSlabBytes = ((kSlabTx + 127) / 128) * 128;
     static constexpr int kAOff = 0;
     static constexpr int kBOff = kAOff + SA * kABytes;
-    static constexpr int kStagingOff = kBOff + SB * kBBytes; // 8 epilogue warps x 2 KB (32 rows x 32 bf16, 64B swizzle)
-    static constexpr int kSlabOff = kStagingOff + kEpiWarps * 2048;
+    // 8 epilogue warps x 2 KB (32 rows x 32 bf16, 64B swizzle); BLOCK_N == 64: x 4 KB (32 rows x 64 bf16, 128B swizzle)
+    static constexpr int kStagingBytes = BLOCK_N == 64 ? 4096 : 2048;
+    static constexpr int kStagingOff = kBOff + SB * kBBytes;
+    static constexpr int kSlabOff = kStagingOff + kEpiWarps * kStagingBytes;
     static constexpr int kBarOff = kSlabOff + SS * kSlabBytes;
     static constexpr int kNumBars = 2 * SS + 2 * SA + 2 * SB + 4;
     static constexpr int kBiasOff = ((kBarOff + kNumBars * 8 + 8 + 15) / 16) * 16;
@@ -118,7 +121,7 @@ template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS, int NH, bool PRO
 __global__ void __launch_bounds__(kSepThreads, 1)
 sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_taps,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
-                const SepParams p) {
+                const __grid_constant__ CUtensorMap map_out64, const SepParams p) {
     using L = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS>;
     constexpr int KSWZ = L::KSWZ;
     constexpr int kMmasPerBlock = CB / 16;
@@ -431,7 +434,7 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         // ===================== epilogue =====================
         const int q = (warp - kEpiWarp0) & 3;                 // TMEM lane quarter == warp % 4
         const int grp = (warp - kEpiWarp0) >> 2;              // NH = 1: accumulator stage; NH = 2: column half
-        unsigned char *stg = smem + L::kStagingOff + (grp * 4 + q) * 2048;
+        unsigned char *stg = smem + L::kStagingOff + (grp * 4 + q) * L::kStagingBytes;
         int local_tile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
             if (NH == 1 && (local_tile & 1) != grp) continue;
@@ -454,6 +457,45 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             if (rbase) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rnext[j] = rbase[j];
+            }
+            if constexpr (BLOCK_N == 64) {
+                if (p.wide64 && p.act == LWOP_ACT_RELU && !p.residual) {
+                    // Cout = 64 (the first separable layer: 1.1 GB of output, epilogue-bound): the whole 64-channel row of
+                    // the tile goes out as ONE 128B-swizzled staging tile and ONE TMA store per warp -- half the
+                    // load / fence / store round trips of the 32-column form.
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(taddr, ra);
+                    tmem_ld_32x32b_x32(taddr + 32u, rb);
+                    tmem_ld_wait();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[grp]);
+                    if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());
+                    __syncwarp();
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t *r = j < 4 ? &ra[j * 8] : &rb[(j - 4) * 8];
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(b0.z, b0.w));
+                        const float2 s2 = fadd2(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(b1.x, b1.y));
+                        const float2 s3 = fadd2(make_float2(__uint_as_float(r[6]), __uint_as_float(r[7])), make_float2(b1.z, b1.w));
+                        uint4 o;
+                        o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
+                        o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
+                        // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                        *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&map_out64, stg, p.out_col0 + n0, tx * kTW, ty * kTH + q * 2, b);
+                        bulk_commit_group();
+                    }
+                    if (pf) pf_acc[PF_EPI_WORK] += (unsigned long long)(clock64() - pf_e0);
+                    continue;
+                }
             }
 #pragma unroll 1
             for (int g = 0; g < BLOCK_N / 32; ++g) {
@@ -948,7 +990,7 @@ sep_pair2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 }  // namespace
 
 struct SepPlan {
-    CUtensorMap map_in, map_taps, map_b, map_out;
+    CUtensorMap map_in, map_taps, map_b, map_out, map_out64;   // map_out64: (64 channels, 16, 2, 1) box, 128B swizzle (Cout_pad == 64)
     SepParams p;
     int block_n, cb, dil, nh;
     int pair;          // CTA-pair kernel (Cout = 512)
@@ -964,12 +1006,12 @@ cudaError_t launch_sep_t(const SepPlan *pl, cudaStream_t s) {
         auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, true>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+        return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->map_out64, pl->p);
     }
     auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, false>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->p);
+    return launch_chain(kfn, (unsigned)pl->grid, kSepThreads, smem, s, 1, pl->map_in, pl->map_taps, pl->map_b, pl->map_out, pl->map_out64, pl->p);
 }
 
 }  // namespace
@@ -1000,6 +1042,8 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
     {
         static const char *pk = getenv("LWOP_SEP_PARK");
         p.park = pk ? (unsigned)atoi(pk) : 1u;
+        static const char *w64 = getenv("LWOP_SEP_WIDE64");
+        p.wide64 = w64 ? atoi(w64) : 1;
     }
     p.dw_w = d.dw_w;
     p.bias = d.bias;
@@ -1063,6 +1107,14 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
         if (!encode_tiled_bf16(&pl->map_out, 4, d.out, dims, strides, box, 64, err, errlen)) {
             free(pl);
             return nullptr;
+        }
+        pl->map_out64 = pl->map_out;
+        if (pl->block_n == 64) {
+            cuuint32_t box64[4] = {64, (cuuint32_t)kTW, 2, 1};
+            if (!encode_tiled_bf16(&pl->map_out64, 4, d.out, dims, strides, box64, 128, err, errlen)) {
+                free(pl);
+                return nullptr;
+            }
         }
     }
     return pl;
