@@ -55,7 +55,7 @@ struct SepParams {
     int act, ldr, out_col0;
     unsigned long long *prof;       // optional [16] stall counters (LWOP_SEP_PROF=1), nullptr otherwise
     unsigned park;                  // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 2 depthwise, 3 epilogue)
-    int wide64;                     // Cout_pad == 64: one 64-column staging tile + TMA store per warp and tile (LWOP_SEP_WIDE64=0: two 32-column ones)
+    int wide64;                     // 64-column staging tiles + TMA stores in the epilogue where the shape allows (LWOP_SEP_WIDE64=0: 32-column ones)
 };
 
 // stall accounting (debugging aid): cycles one elected thread of each role spends in each barrier wait
@@ -73,7 +73,7 @@ enum { PF_TOTAL = 0, PF_TMA_SLAB_EMPTY, PF_TMA_AB_EMPTY, PF_MMA_TMEM_EMPTY, PF_M
         }                                                       \
     } while (0)
 
-template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS>
+template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS, int NH = 1>
 struct SepSmem {
     static constexpr int KSWZ = 2 * CB;                      // bytes per K-major operand row
     static constexpr int kABytes = 128 * KSWZ;
@@ -85,8 +85,10 @@ struct SepSmem {
     static constexpr int kSlabBytes = ((kSlabTx + 127) / 128) * 128;
     static constexpr int kAOff = 0;
     static constexpr int kBOff = kAOff + SA * kABytes;
-    // 8 epilogue warps x 2 KB (32 rows x 32 bf16, 64B swizzle); BLOCK_N == 64: x 4 KB (32 rows x 64 bf16, 128B swizzle)
-    static constexpr int kStagingBytes = BLOCK_N == 64 ? 4096 : 2048;
+    // 8 epilogue warps x 4 KB (32 rows x 64 bf16, 128B swizzle; the 32-column form uses the first 2 KB with a 64B
+    // swizzle); the single-pass Cout = 512 form (NH == 2) only has the 32-column epilogue: 2 KB
+    static constexpr bool kWide = NH == 1 && BLOCK_N >= 64;
+    static constexpr int kStagingBytes = kWide ? 4096 : 2048;
     static constexpr int kStagingOff = kBOff + SB * kBBytes;
     static constexpr int kSlabOff = kStagingOff + kEpiWarps * kStagingBytes;
     static constexpr int kBarOff = kSlabOff + SS * kSlabBytes;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kSepThreads, 1)
 sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_taps,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                 const __grid_constant__ CUtensorMap map_out64, const SepParams p) {
-    using L = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS>;
+    using L = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS, NH>;
     constexpr int KSWZ = L::KSWZ;
     constexpr int kMmasPerBlock = CB / 16;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -458,40 +460,52 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rnext[j] = rbase[j];
             }
-            if constexpr (BLOCK_N == 64) {
-                if (p.wide64 && p.act == LWOP_ACT_RELU && !p.residual) {
-                    // Cout = 64 (the first separable layer: 1.1 GB of output, epilogue-bound): the whole 64-channel row of
-                    // the tile goes out as ONE 128B-swizzled staging tile and ONE TMA store per warp -- half the
-                    // load / fence / store round trips of the 32-column form.
-                    uint32_t ra[32], rb[32];
-                    tmem_ld_32x32b_x32(taddr, ra);
-                    tmem_ld_32x32b_x32(taddr + 32u, rb);
-                    tmem_ld_wait();
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[grp]);
-                    if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());
-                    __syncwarp();
-                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0);
+            if constexpr (L::kWide) {
+                if (p.wide64 && !p.residual && (p.act == LWOP_ACT_RELU || p.act == LWOP_ACT_ELU)) {
+                    // 64 output channels per iteration: ONE 128B-swizzled staging tile and ONE TMA store per warp -- half
+                    // the load / fence / store round trips of the 32-column form, which is what the epilogue-bound
+                    // layers (first layer: 1.1 GB of output; the ELU layers) spend their time on.
+                    const bool elu = p.act == LWOP_ACT_ELU;
+#pragma unroll 1
+                    for (int g = 0; g < BLOCK_N / 64; ++g) {
+                        uint32_t ra[32], rb[32];
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64), ra);
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + 32), rb);
+                        tmem_ld_wait();
+                        if (g == BLOCK_N / 64 - 1) {              // accumulator drained: hand it back to the MMA warp
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[grp]);
+                        }
+                        if (lane == 0) PF_WAIT(PF_EPI_STORE_WAIT, bulk_wait_read_all());
+                        __syncwarp();
+                        const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + n0 + g * 64);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t *r = j < 4 ? &ra[j * 8] : &rb[(j - 4) * 8];
-                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
-                        const float2 s0 = fadd2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(b0.x, b0.y));
-                        const float2 s1 = fadd2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(b0.z, b0.w));
-                        const float2 s2 = fadd2(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(b1.x, b1.y));
-                        const float2 s3 = fadd2(make_float2(__uint_as_float(r[6]), __uint_as_float(r[7])), make_float2(b1.z, b1.w));
-                        uint4 o;
-                        o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
-                        o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
-                        // 128B swizzle: 16-byte chunk index XOR (row & 7)
-                        *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_4d(&map_out64, stg, p.out_col0 + n0, tx * kTW, ty * kTH + q * 2, b);
-                        bulk_commit_group();
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t *r = j < 4 ? &ra[j * 8] : &rb[(j - 4) * 8];
+                            const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                            float2 s0 = fadd2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(b0.x, b0.y));
+                            float2 s1 = fadd2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(b0.z, b0.w));
+                            float2 s2 = fadd2(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), make_float2(b1.x, b1.y));
+                            float2 s3 = fadd2(make_float2(__uint_as_float(r[6]), __uint_as_float(r[7])), make_float2(b1.z, b1.w));
+                            uint4 o;
+                            if (elu) {
+                                s0 = elu2_fast(s0); s1 = elu2_fast(s1); s2 = elu2_fast(s2); s3 = elu2_fast(s3);
+                                o.x = pack_bf16x2(s0.x, s0.y); o.y = pack_bf16x2(s1.x, s1.y);
+                                o.z = pack_bf16x2(s2.x, s2.y); o.w = pack_bf16x2(s3.x, s3.y);
+                            } else {
+                                o.x = pack_relu_bf16x2(s0.x, s0.y); o.y = pack_relu_bf16x2(s1.x, s1.y);
+                                o.z = pack_relu_bf16x2(s2.x, s2.y); o.w = pack_relu_bf16x2(s3.x, s3.y);
+                            }
+                            // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                            *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&map_out64, stg, p.out_col0 + n0 + g * 64, tx * kTW, ty * kTH + q * 2, b);
+                            bulk_commit_group();
+                        }
                     }
                     if (pf) pf_acc[PF_EPI_WORK] += (unsigned long long)(clock64() - pf_e0);
                     continue;
@@ -1001,7 +1015,7 @@ namespace {
 
 template <int BLOCK_N, int CB, int DIL, int SA, int SB, int SS, int NH>
 cudaError_t launch_sep_t(const SepPlan *pl, cudaStream_t s) {
-    constexpr int smem = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS>::kTotal;
+    constexpr int smem = SepSmem<BLOCK_N, CB, DIL, SA, SB, SS, NH>::kTotal;
     if (pl->p.prof) {
         auto kfn = sep_conv_kernel<BLOCK_N, CB, DIL, SA, SB, SS, NH, true>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1109,7 +1123,7 @@ SepPlan *sep_plan_create(const SepConvDesc &d, char *err, size_t errlen) {
             return nullptr;
         }
         pl->map_out64 = pl->map_out;
-        if (pl->block_n == 64) {
+        if (pl->nh == 1 && pl->block_n >= 64) {
             cuuint32_t box64[4] = {64, (cuuint32_t)kTW, 2, 1};
             if (!encode_tiled_bf16(&pl->map_out64, 4, d.out, dims, strides, box64, 128, err, errlen)) {
                 free(pl);
@@ -1160,13 +1174,13 @@ static cudaError_t sep_plan_launch_inner(const SepPlan *pl, cudaStream_t s) {
     // ring depths (A, B, slab): (4,3,3) / (5,3,2) / (4,4,2) measured within 2% of each other
     if (pl->pair) return pl->dil == 2 ? launch_sep_pair2<2, 4, 3, 2>(pl, s) : launch_sep_pair2<1, 4, 3, 3>(pl, s);
     if (pl->cb == 32) return launch_sep_t<64, 32, 1, 2, 3, 6, 1>(pl, s);
-    if (pl->block_n == 128) return launch_sep_t<128, 64, 1, 2, 4, 4, 1>(pl, s);
+    if (pl->block_n == 128) return launch_sep_t<128, 64, 1, 2, 4, 3, 1>(pl, s);
     if (pl->nh == 2) {
         if (pl->dil == 2) return launch_sep_t<256, 64, 2, 2, 3, 2, 2>(pl, s);
         return launch_sep_t<256, 64, 1, 2, 3, 3, 2>(pl, s);
     }
-    if (pl->dil == 2) return launch_sep_t<256, 64, 2, 2, 3, 2, 1>(pl, s);
-    return launch_sep_t<256, 64, 1, 2, 3, 3, 1>(pl, s);
+    if (pl->dil == 2) return launch_sep_t<256, 64, 2, 2, 2, 2, 1>(pl, s);
+    return launch_sep_t<256, 64, 1, 2, 3, 2, 1>(pl, s);
 }
 
 }  // namespace lwop
