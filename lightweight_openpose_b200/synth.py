@@ -179,3 +179,34 @@ def synth_scene(seed: int, num_persons: int, height: int = 368, width: int = 368
         heat = heat + rng.uniform(0.0, noise, size=heat.shape).astype(np.float32)
         paf = paf + rng.normal(0.0, noise / 2, size=paf.shape).astype(np.float32)
     return heat.astype(np.float32), paf.astype(np.float32), kps
+
+
+# joint types joined by each limb: joint_to_limb_heatmap_relationship of the 14-joint variant (src/pose_decode.py:16-17)
+_LIMB_JOINTS = [[0, 1], [1, 2], [3, 4], [4, 5], [6, 7], [7, 8], [9, 10], [10, 11], [12, 13], [13, 0], [13, 3], [13, 6],
+                [13, 9]]
+
+
+def random_limb_tables(seed, joints_per_type, density):
+    """Adversarial input of the grouping stage: random connections between random joints, every source joint at most
+    once per limb type (what find_connected_joints emits), destinations may repeat (:295 keeps them)."""
+    rng = np.random.default_rng(seed)
+    rows, nid = [], 0
+    ids = []
+    for jt in range(14):
+        n = int(joints_per_type)
+        ids.append(np.arange(nid, nid + n))
+        for _ in range(n):
+            rows.append((float(rng.integers(0, 368)), float(rng.integers(0, 368)), float(np.float32(rng.uniform(0.1, 1.0))),
+                         float(nid), 0.0, float(jt)))
+            nid += 1
+    joint_list = np.array(rows, dtype=np.float64).reshape(-1, 6)
+    limbs = []
+    for t in range(13):
+        ja, jb = _LIMB_JOINTS[t]
+        out = []
+        for i, a in enumerate(ids[ja]):
+            if rng.uniform() < density and len(ids[jb]):
+                j = int(rng.integers(0, len(ids[jb])))
+                out.append((float(a), float(ids[jb][j]), float(rng.uniform(0.05, 1.0)), float(i), float(j)))
+        limbs.append(np.array(out, dtype=np.float64).reshape(-1, 5))
+    return limbs, joint_list

@@ -189,3 +189,37 @@ def test_nms_gaussian_patch_filter(decode_golden_noipp):
         _lists_equal(got, want, tol=0.0)
         # without centre refinement the flag has no effect, as in the reference
         _lists_equal(pose_decode.NMS(PARAM, heat, 8.0, False, True), orc.refine_peaks(heat, PARAM["thre1"], 8.0, refine=False), tol=0.0)
+
+
+@pytest.mark.parametrize("spec", [(1, 6, 0.9), (2, 20, 0.7), (3, 40, 0.5), (4, 60, 0.35), (5, 100, 0.25), (6, 3, 1.0)])
+def test_grouping_on_adversarial_tables(spec):
+    """The grouping kernel on random connection tables (repeated destinations, merges, >= 3 matches, list.pop): up
+    to ~300 working persons, i.e. beyond the 128 rows the kernel keeps in shared memory (global spill path)."""
+    seed, n, dens = spec
+    limbs, joint_list = synth.random_limb_tables(seed, n, dens)
+    want = orc.group_persons(limbs, joint_list)
+    got = pose_decode.group_limbs_of_same_person(limbs, joint_list)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if want.size:
+        assert np.array_equal(got[:, :14], want[:, :14]) and np.array_equal(got[:, 15], want[:, 15])
+        assert np.abs(got[:, 14] - want[:, 14]).max() <= 1e-9
+
+
+def test_capacity_limits_fail_loudly():
+    """The device tables have fixed capacities the reference does not have (128 peaks per joint channel, 128 persons):
+    exceeding one is an error, never a silently truncated result."""
+    from lightweight_openpose_b200 import _lib
+    heat = np.zeros((96, 96, 14), np.float32)
+    heat[3::6, 3::6, 0] = 0.9                       # 16 x 16 = 256 isolated peaks, 6 px apart (> the radius-5 suppression)
+    assert len(orc.greedy_radius_peaks(heat[:, :, 0], 0.1)) == 256
+    with pytest.raises(_lib.LwopError):
+        pose_decode.NMS(PARAM, heat, 8.0)
+    with pytest.raises(_lib.LwopError):
+        pose_decode.decode_pose(np.zeros((768, 768, 3), np.uint8), PARAM, heat, np.zeros((96, 96, 26), np.float32))
+    heat[:, :, 0] = 0.0
+    heat[3::12, 3::6, 0] = 0.9                      # 8 x 16 = 128 peaks: exactly the capacity, no error
+    got = pose_decode.NMS(PARAM, heat, 8.0)
+    assert len(got[0]) == 128 and all(len(g) == 0 for g in got[1:])
+    eng = engine.Engine(64, 64, max_batch=2, device=0)
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros((3, 64, 64, 3), device="cuda"))

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import decode_oracle as orc
+from lightweight_openpose_b200 import synth
 from lightweight_openpose_b200.synth import synth_scene
 
 FLOAT_TOL = 1e-5
@@ -186,3 +187,24 @@ def test_oracle_gaussian_nms_matches_reference_golden(decode_golden_noipp, decod
                     # a last-ulp difference of IPP's patch resize can move the argmax of the smoothed (flat-topped) patch by a pixel
                     assert np.abs(rows[:, :2] - want[:, :2]).max() <= 1 and np.array_equal(rows[:, 3:], want[:, 3:]), name
                     assert np.abs(rows[:, 2] - want[:, 2]).max() <= tol, name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_grouping_restatement_on_adversarial_tables_matches_live_reference():
+    """group_limbs_of_same_person (:304-396) on random connection tables: repeated destinations, two-person merges,
+    >= 3 matches (-> new person), long person lists (list.pop far down the list) -- cases natural scenes rarely hit."""
+    import warnings
+    sys.path.insert(0, "/root/reference")
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from src import pose_decode as ref
+    finally:
+        sys.path.remove("/root/reference")
+    for seed, n, dens in ((1, 6, 0.9), (2, 20, 0.7), (3, 40, 0.5), (4, 60, 0.35), (5, 100, 0.25), (6, 3, 1.0)):
+        limbs, joint_list = synth.random_limb_tables(seed, n, dens)
+        want = np.asarray(ref.group_limbs_of_same_person([l if len(l) else [] for l in limbs], joint_list))
+        got = orc.group_persons(limbs, joint_list)
+        assert got.shape == want.shape, (seed, got.shape, want.shape)
+        if want.size:
+            assert np.array_equal(got, want), seed
