@@ -160,6 +160,10 @@ SEP_CASES = [
     (1, 23, 37, 128, 128, 1, 2, False),      # odd, non-square, patches clipped at the border
     (1, 7, 5, 64, 256, 2, 1, False),         # map smaller than one patch
     (5, 16, 32, 128, 256, 1, 0, False),      # exact patches, linear
+    (1, 23, 37, 512, 512, 1, 1, False),      # CTA-pair kernel: 9 tiles (odd: the last pair holds a dummy patch), clipped patches
+    (3, 8, 16, 256, 512, 1, 1, False),       # CTA-pair kernel: 3 exact tiles, one K group
+    (1, 7, 5, 512, 512, 2, 1, False),        # a single tile: falls back to the single-CTA Cout = 512 form
+    (2, 46, 46, 128, 128, 1, 2, False),      # ELU without tf.add: 64-column epilogue
 ]
 
 
