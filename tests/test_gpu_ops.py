@@ -198,7 +198,9 @@ def test_fused_separable_kernel(eng, case):
     assert err.max() <= tol, (err.max(), tol, np.unravel_index(err.argmax(), err.shape))
 
 
-@pytest.mark.parametrize("case", [(2 * 46 * 46, 512), (3 * 23 * 37, 128), (128, 512), (5, 128), (2 * 46 * 46 + 77, 128)])
+@pytest.mark.parametrize("case", [(2 * 46 * 46, 512), (3 * 23 * 37, 128), (128, 512), (5, 128), (2 * 46 * 46 + 77, 128),
+                                  # several tiles per CTA: the cross-tile MMA schedule, both acc2 stages, ragged last tile
+                                  (148 * 3 * 128 + 50, 512), (148 * 5 * 128, 128)])
 def test_fused_head_pair_kernel(eng, case):
     """Two 2-layer 1x1 heads on one input as ONE back-to-back GEMM kernel (initial-stage heads 128->512->14|26,
     refinement heads 128->128->14|26): float64 reference with the hidden activations rounded to bf16, which is
