@@ -78,6 +78,8 @@ TC_CASES = [
     (2, 46, 46, 128, 128, 3, 2, 1, True, False),     # dilation 2 + residual
     (3, 23, 37, 128, 128, 3, 2, 1, False, False),    # non-square, image-boundary-crossing tiles
     (1, 7, 5, 128, 128, 3, 1, 1, False, False),      # tiny tensor (< 128 KiB im2col map workaround)
+    (40, 46, 46, 128, 128, 3, 1, 1, True, False),    # CTA-pair GEMM: several 512-row pair tiles per cluster, both TMEM stages
+    (40, 46, 46, 512, 128, 1, 1, 1, False, False),   # CTA-pair GEMM, 1x1, deep K
 ]
 
 
