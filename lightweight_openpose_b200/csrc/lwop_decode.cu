@@ -195,12 +195,23 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
         __shared__ float s_wv[8];
         __shared__ int s_wp[8];
         __shared__ int s_best_p;
+        // Each thread owns candidates tid, tid + 256, ...: it drops those within the radius of the peak kept in the
+        // previous round and takes the arg-max of its survivors in the same pass (no barrier between the two).
+        int prev = -1, prev_y = 0, prev_x = 0;
         while (true) {
             float bv = -INFINITY;
             int bp = -1;
             for (int i = tid; i < nc; i += blockDim.x) {
                 const int p = cand[i];
                 if (p < 0) continue;
+                if (prev >= 0) {
+                    const int py = p / w, px = p - py * w;
+                    const int dy = py - prev_y, dx = px - prev_x;
+                    if (dx * dx + dy * dy <= kRadius * kRadius) {          // keeps dis > dis_thres (:68); drops `prev` too
+                        cand[i] = -1;
+                        continue;
+                    }
+                }
                 const float v = val[p];
                 if (v > bv || (v == bv && p > bp)) { bv = v; bp = p; }
             }
@@ -228,15 +239,9 @@ peaks_kernel(const float *__restrict__ heat, int h, int w, int C, float thre1, d
                 break;
             }
             ++n;
-            const int by = best / w, bx = best - by * w;
-            for (int i = tid; i < nc; i += blockDim.x) {
-                const int p = cand[i];
-                if (p < 0) continue;
-                const int py = p / w, px = p - py * w;
-                const int dy = py - by, dx = px - bx;
-                if (dx * dx + dy * dy <= kRadius * kRadius) cand[i] = -1;   // keeps dis > dis_thres (:68); drops `best` too
-            }
-            __syncthreads();
+            prev = best;
+            prev_y = best / w;
+            prev_x = best - prev_y * w;
         }
     }
     if (tid == 0) peak_counts[b * 16 + ch] = n;
