@@ -21,5 +21,5 @@ for _ in range(3):
 acc /= 3
 for d, ms in zip(descs, acc):
     if d[9] == 4:
-        print("debug", os.environ.get("LWOP_HEADS_DEBUG"), "layer", d[0], "hidden", d[5], "ms %.4f" % ms)
+        print("head pair layer", d[0], "hidden", d[5], "ms %.4f" % ms)
 print("forward sum ms %.3f" % acc.sum())
