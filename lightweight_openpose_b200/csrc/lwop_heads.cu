@@ -83,6 +83,10 @@ enum { HP_TOTAL = 0, HP_MMA_X, HP_MMA_ACC1_EMPTY, HP_MMA_W1, HP_MMA_A2_FULL, HP_
 constexpr uint32_t kAcc2Col = 256, kAcc2Stride = 64, kAcc2OffB = 32;
 constexpr uint32_t kA2TmemCol = 384;
 
+// PAIR: the two CTAs of a cluster take two row tiles and issue every MMA as one cta_group::2 instruction (M = 256): each
+// CTA stages only half of every weight tile (64 of the 128 W1 rows, 8 / 16 of the W2 rows), which is what the
+// N = 128 first GEMM is short of -- its operand reads alone fill the shared-memory pipe in the single-CTA form.
+template <bool PAIR>
 __global__ void __launch_bounds__(kHpThreads, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1a,
                  const __grid_constant__ CUtensorMap map_w1b, const __grid_constant__ CUtensorMap map_w2a,
@@ -112,6 +116,14 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const int P = p.passes, half = P / 2;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    // work units: row tiles (single CTA) or pairs of row tiles (cluster); this CTA's tile of unit u is u * 2 + rank
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_units = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    constexpr int kW1Rows = PAIR ? 64 : 128;                 // W1 rows this CTA stages per chunk
+    constexpr uint32_t kW1Tx = PAIR ? 2 * (L::kW1Bytes / 2) : L::kW1Bytes;
     unsigned long long hp_acc[HP_N];
 #pragma unroll
     for (int i = 0; i < HP_N; ++i) hp_acc[i] = 0;
@@ -130,21 +142,25 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int i = 0; i < kW2Stages; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc1_full[i], 1);
-            mbar_init(&acc1_empty[i], 4);
-            mbar_init(&a2_full[i], 4);
+            mbar_init(&acc1_empty[i], PAIR ? 8 : 4);
+            mbar_init(&a2_full[i], PAIR ? 8 : 4);
             mbar_init(&a2_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc2_full[i], 1);
-            mbar_init(&acc2_empty[i], 4);
+            mbar_init(&acc2_empty[i], PAIR ? 8 : 4);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_ptr);
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_alloc_2sm<512>(tmem_ptr);
+        else tmem_alloc<512>(tmem_ptr);
+    }
     for (int i = threadIdx.x; i < 2 * p.K2; i += kHpThreads) bias1_s[i] = i < p.K2 ? p.b1a[i] : p.b1b[i - p.K2];
     for (int i = threadIdx.x; i < 48; i += kHpThreads) bias2_s[i] = i < 16 ? p.b2a[i] : p.b2b[i - 16];
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
@@ -155,14 +171,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) {
             int ws = 0;
             uint32_t wph = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            for (int u = unit0; u < num_units; u += unit_step) {
                 for (int pp = 0; pp < P; ++pp) {
                     const CUtensorMap *mw = pp < half ? &map_w1a : &map_w1b;
-                    const int row0 = (pp < half ? pp : pp - half) * 128;
+                    const int row0 = (pp < half ? pp : pp - half) * 128 + rank * kW1Rows;
                     for (int kc = 0; kc < 2; ++kc) {
                         mbar_wait_sel(&w1_empty[ws], wph ^ 1, p.park & 1u);
-                        mbar_arrive_expect_tx(&w1_full[ws], L::kW1Bytes);
-                        tma_load_2d(smem + L::kW1Off + ws * L::kW1Bytes, mw, &w1_full[ws], kc * 64, row0);
+                        if (leader) mbar_arrive_expect_tx(&w1_full[ws], kW1Tx);
+                        if constexpr (PAIR) tma_load_2d_2sm(smem + L::kW1Off + ws * L::kW1Bytes, mw, &w1_full[ws], kc * 64, row0);
+                        else tma_load_2d(smem + L::kW1Off + ws * L::kW1Bytes, mw, &w1_full[ws], kc * 64, row0);
                         if (++ws == kW1Stages) { ws = 0; wph ^= 1; }
                     }
                 }
@@ -173,11 +190,17 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) {
             int xs = 0;
             uint32_t xph = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            for (int u = unit0; u < num_units; u += unit_step) {
+                const int tile = PAIR ? u * 2 + rank : u;       // a dummy tile past the end loads zeros (TMA OOB fill)
                 mbar_wait_sel(&x_empty[xs], xph ^ 1, p.park & 1u);
-                mbar_arrive_expect_tx(&x_full[xs], L::kXBytes);
-                tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
-                tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
+                if (leader) mbar_arrive_expect_tx(&x_full[xs], (PAIR ? 2 : 1) * L::kXBytes);
+                if constexpr (PAIR) {
+                    tma_load_2d_2sm(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
+                    tma_load_2d_2sm(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
+                } else {
+                    tma_load_2d(smem + L::kXOff + xs * L::kXBytes, &map_x, &x_full[xs], 0, tile * 128);
+                    tma_load_2d(smem + L::kXOff + xs * L::kXBytes + 16384, &map_x, &x_full[xs], 64, tile * 128);
+                }
                 if (++xs == kXStages) { xs = 0; xph ^= 1; }
             }
         }
@@ -186,16 +209,22 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) {
             int ws = 0;
             uint32_t wph = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            for (int u = unit0; u < num_units; u += unit_step) {
                 for (int pp = 0; pp < P; ++pp) {
                     const bool is_a = pp < half;
                     const int k0 = (is_a ? pp : pp - half) * 128;
-                    const uint32_t bytes = is_a ? 2 * 16 * 128 : 2 * 32 * 128;
+                    const uint32_t bytes = is_a ? 2 * 16 * 128 : 2 * 32 * 128;      // both K chunks, all rows (of both CTAs)
+                    const int r0 = PAIR ? rank * (is_a ? 8 : 16) : 0;               // PAIR: this CTA stages half of the rows
                     mbar_wait_sel(&w2_empty[ws], wph ^ 1, p.park & 1u);
-                    mbar_arrive_expect_tx(&w2_full[ws], bytes);
+                    if (leader) mbar_arrive_expect_tx(&w2_full[ws], bytes);
                     unsigned char *dst = smem + L::kW2Off + ws * L::kW2Bytes;
-                    tma_load_2d(dst, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0, 0);
-                    tma_load_2d(dst + 4096, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0 + 64, 0);
+                    if constexpr (PAIR) {
+                        tma_load_2d_2sm(dst, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0, r0);
+                        tma_load_2d_2sm(dst + 4096, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0 + 64, r0);
+                    } else {
+                        tma_load_2d(dst, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0, 0);
+                        tma_load_2d(dst + 4096, is_a ? &map_w2a : &map_w2b, &w2_full[ws], k0 + 64, 0);
+                    }
                     if (++ws == kW2Stages) { ws = 0; wph ^= 1; }
                 }
             }
@@ -203,9 +232,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues.
-        constexpr uint32_t kIdesc1 = make_idesc_bf16(128, 128);
-        constexpr uint32_t kIdescA = make_idesc_bf16(128, 16);
-        constexpr uint32_t kIdescB = make_idesc_bf16(128, 32);
+        constexpr uint32_t kIdesc1 = make_idesc_bf16(PAIR ? 256 : 128, 128);
+        constexpr uint32_t kIdescA = make_idesc_bf16(PAIR ? 256 : 128, 16);
+        constexpr uint32_t kIdescB = make_idesc_bf16(PAIR ? 256 : 128, 32);
+        // PAIR: only the leader CTA's warp walks the schedule; its commits arrive in both CTAs
+        auto commit = [&](uint64_t *bar) {
+            if constexpr (PAIR) umma_commit_2sm(bar, 3);
+            else umma_commit(bar);
+        };
+        if (leader) {
         int xs = 0, w1s = 0, w2s = 0;
         uint32_t xph = 0, w1ph = 0, w2ph = 0;
         uint32_t use0 = 0, use1 = 0;       // uses of acc1 stage 0 / 1 (MMA1), phase bookkeeping
@@ -231,13 +266,18 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 for (int kc = 0; kc < 2; ++kc) {
                     const uint64_t db = make_kmajor_desc<128>(w2 + kc * 4096);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ts(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
-                                     (kslice | kc | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (PAIR)
+                            umma_bf16_ts_2sm(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2),
+                                             is_a ? kIdescA : kIdescB, (kslice | kc | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16_ts(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
+                                         (kslice | kc | k) != 0 ? 1u : 0u);
+                    }
                 }
-                umma_commit(&a2_empty[buf]);
-                umma_commit(&w2_empty[w2s]);
-                if (pp == P - 1) umma_commit(&acc2_full[st]);
+                commit(&a2_empty[buf]);
+                commit(&w2_empty[w2s]);
+                if (pp == P - 1) commit(&acc2_full[st]);
             }
             __syncwarp();
             if (buf) ++useb1; else ++useb0;
@@ -246,7 +286,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         };
         int issued1 = 0;                   // MMA1 passes issued so far
         int local_tile = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
+        for (int u = unit0; u < num_units; u += unit_step, ++local_tile) {
             HP_WAIT(HP_MMA_X, mbar_wait_sel(&x_full[xs], xph, p.park & 2u));
             const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
             for (int pp = 0; pp < P; ++pp) {
@@ -262,12 +302,16 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         const uint64_t da = make_kmajor_desc<128>(xa + kc * 16384);
                         const uint64_t db = make_kmajor_desc<128>(smem_u32(smem + L::kW1Off + w1s * L::kW1Bytes));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16_ss(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
-                        umma_commit(&w1_empty[w1s]);
+                        for (int k = 0; k < 4; ++k) {
+                            if constexpr (PAIR)
+                                umma_bf16_ss_2sm(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16_ss(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                        }
+                        commit(&w1_empty[w1s]);
                         if (kc == 1) {
-                            umma_commit(&acc1_full[s]);
-                            if (pp == P - 1) umma_commit(&x_empty[xs]);
+                            commit(&acc1_full[s]);
+                            if (pp == P - 1) commit(&x_empty[xs]);
                         }
                     }
                     __syncwarp();
@@ -279,12 +323,18 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (++xs == kXStages) { xs = 0; xph ^= 1; }
         }
         while (m2_tile < local_tile) mma2();     // the two (or fewer) passes still in flight
+        }
     } else if (warp >= kHpEpiWarp0) {
         // ===================== epilogue groups =====================
         const int q = (warp - kHpEpiWarp0) & 3;               // TMEM lane quarter == warp % 4
         const int grp = (warp - kHpEpiWarp0) >> 2;            // owns acc1 stage / A2 buffer `grp`
         const int row = q * 32 + lane;                        // row of the tile == TMEM lane
         uint32_t use = 0;
+        // releases go to the MMA thread: the leader CTA's copy of the barrier in the PAIR form
+        auto arrive = [&](uint64_t *bar) {
+            if constexpr (PAIR) mbar_arrive_leader(bar);
+            else mbar_arrive(bar);
+        };
         // ---- epilogue-2: the two narrow linear outputs of a tile (group 0; acc2 stage = local tile & 1) ----
         auto epilogue2 = [&](int lt, int tile) {
             const int st = lt & 1;
@@ -298,7 +348,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc2_empty[st]);
+            if (lane == 0) arrive(&acc2_empty[st]);
             const long long m = (long long)tile * 128 + row;
             if (m < p.M) {
                 float va[14], vb[26];
@@ -327,7 +377,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (p.prof) hp_acc[HP_E2_WORK] += (unsigned long long)(clock64() - hp_e2);
         };
         int local_tile = 0, prev_tile = -1;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++local_tile) {
+        for (int u = unit0; u < num_units; u += unit_step, ++local_tile) {
+            const int tile = PAIR ? u * 2 + rank : u;
             for (int pp = grp; pp < P; pp += 2, ++use) {
                 HP_WAIT(HP_E_ACC1_FULL, mbar_wait_sel(&acc1_full[grp], use & 1, p.park & 8u));
                 tcgen05_fence_after();
@@ -342,7 +393,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     if (c == 3) {                             // accumulator stage drained
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc1_empty[grp]);
+                        if (lane == 0) arrive(&acc1_empty[grp]);
                     }
                     const float4 *bs4 = reinterpret_cast<const float4 *>(b1 + c * 32);
                     uint32_t pk[16];
@@ -372,7 +423,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();                                  // orders the lanes' stores before lane 0's release
-                if (lane == 0) mbar_arrive(&a2_full[grp]);
+                if (lane == 0) arrive(&a2_full[grp]);
                 if (p.prof) hp_acc[HP_E1_WORK] += (unsigned long long)(clock64() - hp_e0);
                 // the previous tile's outputs: its last MMA2 is issued two passes into this tile, so group 0 drains
                 // acc2 after its first pass here instead of stalling the new tile's accumulator stage
@@ -390,9 +441,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's tensor cores may still read this CTA's operands / write its TMEM
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -402,6 +455,7 @@ struct HeadPairPlan {
     CUtensorMap map_x, map_w1a, map_w1b, map_w2a, map_w2b;
     HpParams p;
     int grid;
+    int pair;        // cta_group::2 form: clusters of two CTAs, weight boxes of half the rows
 };
 
 bool head_pair_supported(int cin, int hidden) { return cin == 128 && (hidden == 512 || hidden == 128); }
@@ -428,6 +482,14 @@ HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t err
     int sms = gemm_num_sms();
     if (sms <= 0) sms = 148;
     pl->grid = p.num_m_tiles < sms ? p.num_m_tiles : sms;
+    {
+        static const char *pe = getenv("LWOP_HEADS_PAIR");
+        pl->pair = ((pe ? atoi(pe) != 0 : true) && p.num_m_tiles >= 4) ? 1 : 0;
+        if (pl->pair) {
+            const int units = (p.num_m_tiles + 1) / 2;
+            pl->grid = 2 * (units < sms / 2 ? units : sms / 2);
+        }
+    }
     bool ok = true;
     {
         cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)d.M};
@@ -438,14 +500,14 @@ HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t err
     for (int hsel = 0; hsel < 2 && ok; ++hsel) {
         cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)d.hidden};
         cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
-        cuuint32_t box[2] = {64, 128};
+        cuuint32_t box[2] = {64, (cuuint32_t)(pl->pair ? 64 : 128)};
         ok = encode_tiled_bf16(hsel ? &pl->map_w1b : &pl->map_w1a, 2, hsel ? d.w1b : d.w1a, dims, strides, box, 128,
                                err, errlen);
     }
     for (int hsel = 0; hsel < 2 && ok; ++hsel) {
         cuuint64_t dims[2] = {(cuuint64_t)d.hidden, (cuuint64_t)(hsel ? 32 : 16)};
         cuuint64_t strides[1] = {(cuuint64_t)d.hidden * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)(hsel ? 32 : 16)};
+        cuuint32_t box[2] = {64, (cuuint32_t)((hsel ? 32 : 16) / (pl->pair ? 2 : 1))};
         ok = encode_tiled_bf16(hsel ? &pl->map_w2b : &pl->map_w2a, 2, hsel ? d.w2b : d.w2a, dims, strides, box, 128,
                                err, errlen);
     }
@@ -459,7 +521,8 @@ HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t err
 void head_pair_plan_destroy(HeadPairPlan *p) { free(p); }
 
 cudaError_t head_pair_plan_launch(const HeadPairPlan *pl, cudaStream_t s, float *out_a_override, float *out_b_override) {
-    cudaError_t e = cudaFuncSetAttribute(head_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HpSmem::kTotal);
+    auto kfn = pl->pair ? head_pair_kernel<true> : head_pair_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, HpSmem::kTotal);
     if (e != cudaSuccess) return e;
     HpParams p = pl->p;
     if (out_a_override) p.out_a = out_a_override;
@@ -473,8 +536,8 @@ cudaError_t head_pair_plan_launch(const HeadPairPlan *pl, cudaStream_t s, float 
         cudaMalloc(&d, sizeof(hbuf));
         cudaMemsetAsync(d, 0, sizeof(hbuf), s);
         p.prof = d;
-        head_pair_kernel<<<pl->grid, kHpThreads, HpSmem::kTotal, s>>>(pl->map_x, pl->map_w1a, pl->map_w1b, pl->map_w2a,
-                                                                     pl->map_w2b, p);
+        launch_chain(kfn, (unsigned)pl->grid, kHpThreads, HpSmem::kTotal, s, pl->pair ? 2 : 1, pl->map_x, pl->map_w1a, pl->map_w1b,
+                     pl->map_w2a, pl->map_w2b, p);
         cudaStreamSynchronize(s);
         cudaMemcpy(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost);
         cudaFree(d);
@@ -483,7 +546,7 @@ cudaError_t head_pair_plan_launch(const HeadPairPlan *pl, cudaStream_t s, float 
         fprintf(stderr, "\n");
         return cudaGetLastError();
     }
-    return launch_chain(head_pair_kernel, (unsigned)pl->grid, kHpThreads, HpSmem::kTotal, s, 1, pl->map_x, pl->map_w1a, pl->map_w1b,
+    return launch_chain(kfn, (unsigned)pl->grid, kHpThreads, HpSmem::kTotal, s, pl->pair ? 2 : 1, pl->map_x, pl->map_w1a, pl->map_w1b,
                         pl->map_w2a, pl->map_w2b, p);
 }
 
