@@ -20,8 +20,8 @@
 //             whose bandwidth the N = 128 MMA1 operand reads already use up)
 // so MMA1(p+1) overlaps epilogue-1(p), and the two epilogue groups alternate passes.
 //   epilogue-2 (group 0): acc2 -> +bias -> fp32 maps and/or the bf16 concat buffer.
-// warp 0: TMA producer for X tiles and W1 chunks; warp 3: TMA producer for W2 slices; warp 1: MMA issuer;
-// warp 2: TMEM allocator; warps 4-11: epilogue groups.
+// warp 0: TMA producer for W1 chunks; warp 2: TMEM allocator, then TMA producer for X tiles; warp 3: TMA producer for
+// W2 slices; warp 1: MMA1 issuer; warp 12: MMA2 issuer; warps 4-11: epilogue groups.
 #include <stdlib.h>
 
 #include "lwop_kernels.cuh"
@@ -30,7 +30,8 @@ namespace lwop {
 
 namespace {
 
-constexpr int kHpThreads = 384;
+constexpr int kHpThreads = 416;            // 4 control warps, 8 epilogue warps, 1 MMA2 issuer
+constexpr int kHpMma2Warp = 12;
 constexpr int kHpEpiWarp0 = 4;
 constexpr int kW1Stages = 6;                  // [128 x 64] bf16 chunks, 16 KB each
 constexpr int kW2Stages = 4;                  // [<=32 x 128] bf16 slices as two 4 KB K-chunks
@@ -166,6 +167,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     pdl_wait();                  // the previous kernel of the chain has completed: its output may be read, our output written
     pdl_launch_dependents();     // the next kernel may start its prologue while this one runs
 
+    // PAIR: commits of the leader's MMA threads arrive on the barrier at the same offset in both CTAs
+    auto commit = [&](uint64_t *bar) {
+        if constexpr (PAIR) umma_commit_2sm(bar, 3);
+        else umma_commit(bar);
+    };
     if (warp == 0) {
         // ===================== TMA producer: first-layer weight chunks (one stream across all tiles) =====================
         if (lane == 0) {
@@ -230,101 +236,101 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA1 issuer: acc1[p & 1] = X * W1[pass p]^T =====================
         // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues.
+        // MMA1 and MMA2 have their own issuing warps: a single warp walking both instruction streams (~200 mostly
+        // dependent instructions per pass) was itself the bottleneck -- the tensor pipe needs ~750 clocks per pass
+        // (tools/ubench/umma_rate.cu, mixed shapes), the one-warp schedule took ~1200.
         constexpr uint32_t kIdesc1 = make_idesc_bf16(PAIR ? 256 : 128, 128);
+        if (leader) {                      // PAIR: only the leader CTA issues; its commits arrive in both CTAs
+            int xs = 0, w1s = 0;
+            uint32_t xph = 0, w1ph = 0;
+            uint32_t use0 = 0, use1 = 0;   // uses of acc1 stage 0 / 1, phase bookkeeping
+            for (int u = unit0; u < num_units; u += unit_step) {
+                HP_WAIT(HP_MMA_X, mbar_wait_sel(&x_full[xs], xph, p.park & 2u));
+                const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
+                for (int pp = 0; pp < P; ++pp) {
+                    const int s = pp & 1;
+                    HP_WAIT(HP_MMA_ACC1_EMPTY, mbar_wait_sel(&acc1_empty[s], ((s ? use1 : use0) & 1) ^ 1, p.park & 2u));
+                    tcgen05_fence_after();
+                    const uint32_t d1 = tmem_base + (uint32_t)(s * 128);
+#pragma unroll
+                    for (int kc = 0; kc < 2; ++kc) {
+                        HP_WAIT(HP_MMA_W1, mbar_wait_sel(&w1_full[w1s], w1ph, p.park & 2u));
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = make_kmajor_desc<128>(xa + kc * 16384);
+                            const uint64_t db = make_kmajor_desc<128>(smem_u32(smem + L::kW1Off + w1s * L::kW1Bytes));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if constexpr (PAIR)
+                                    umma_bf16_ss_2sm(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                                else
+                                    umma_bf16_ss(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                            }
+                            commit(&w1_empty[w1s]);
+                            if (kc == 1) {
+                                commit(&acc1_full[s]);
+                                if (pp == P - 1) commit(&x_empty[xs]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++w1s == kW1Stages) { w1s = 0; w1ph ^= 1; }
+                    }
+                    if (s) ++use1; else ++use0;
+                }
+                if (++xs == kXStages) { xs = 0; xph ^= 1; }
+            }
+        }
+    } else if (warp == kHpMma2Warp) {
+        // ===================== MMA2 issuer: acc2_head += A2[p & 1] (tensor memory) * W2_head[:, K slice p]^T =====================
         constexpr uint32_t kIdescA = make_idesc_bf16(PAIR ? 256 : 128, 16);
         constexpr uint32_t kIdescB = make_idesc_bf16(PAIR ? 256 : 128, 32);
-        // PAIR: only the leader CTA's warp walks the schedule; its commits arrive in both CTAs
-        auto commit = [&](uint64_t *bar) {
-            if constexpr (PAIR) umma_commit_2sm(bar, 3);
-            else umma_commit(bar);
-        };
         if (leader) {
-        int xs = 0, w1s = 0, w2s = 0;
-        uint32_t xph = 0, w1ph = 0, w2ph = 0;
-        uint32_t use0 = 0, use1 = 0;       // uses of acc1 stage 0 / 1 (MMA1), phase bookkeeping
-        uint32_t useb0 = 0, useb1 = 0;     // uses of A2 buffer 0 / 1 (MMA2)
-        // MMA2 runs TWO passes behind MMA1 in one flat schedule over all tiles of this CTA: when MMA2(m) is issued the
-        // epilogue of pass m finished a whole pass ago, so the MMA thread does not sit on the epilogue's latency and the
-        // tensor pipe keeps working on MMA1(m + 1), MMA1(m + 2) meanwhile.  acc2 is double-buffered for the same reason.
-        int m2_tile = 0, m2_pp = 0;        // (local tile, pass) of the next MMA2
-        auto mma2 = [&]() {
-            const int pp = m2_pp, buf = pp & 1, st = m2_tile & 1;
-            HP_WAIT(HP_MMA_A2_FULL, mbar_wait_sel(&a2_full[buf], (buf ? useb1 : useb0) & 1, p.park & 2u));
-            if (pp == 0) HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(&acc2_empty[st], (uint32_t)(((m2_tile >> 1) & 1) ^ 1), p.park & 2u));
-            HP_WAIT(HP_MMA_W2, mbar_wait_sel(&w2_full[w2s], w2ph, p.park & 2u));
-            tcgen05_fence_after();
-            const bool is_a = pp < half;
-            const int kslice = is_a ? pp : pp - half;
-            const uint32_t d = tmem_base + kAcc2Col + (uint32_t)st * kAcc2Stride + (is_a ? 0u : kAcc2OffB);
-            const uint32_t w2 = smem_u32(smem + L::kW2Off + w2s * L::kW2Bytes);
-            if (elect_one()) {
-                // A operand = the hidden activations the epilogue wrote back to tensor memory (no shared-memory round trip)
-                const uint32_t a2t = tmem_base + kA2TmemCol + (uint32_t)(buf * 64);
-#pragma unroll
-                for (int kc = 0; kc < 2; ++kc) {
-                    const uint64_t db = make_kmajor_desc<128>(w2 + kc * 4096);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if constexpr (PAIR)
-                            umma_bf16_ts_2sm(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2),
-                                             is_a ? kIdescA : kIdescB, (kslice | kc | k) != 0 ? 1u : 0u);
-                        else
-                            umma_bf16_ts(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2), is_a ? kIdescA : kIdescB,
-                                         (kslice | kc | k) != 0 ? 1u : 0u);
-                    }
-                }
-                commit(&a2_empty[buf]);
-                commit(&w2_empty[w2s]);
-                if (pp == P - 1) commit(&acc2_full[st]);
-            }
-            __syncwarp();
-            if (buf) ++useb1; else ++useb0;
-            if (++w2s == kW2Stages) { w2s = 0; w2ph ^= 1; }
-            if (++m2_pp == P) { m2_pp = 0; ++m2_tile; }
-        };
-        int issued1 = 0;                   // MMA1 passes issued so far
-        int local_tile = 0;
-        for (int u = unit0; u < num_units; u += unit_step, ++local_tile) {
-            HP_WAIT(HP_MMA_X, mbar_wait_sel(&x_full[xs], xph, p.park & 2u));
-            const uint32_t xa = smem_u32(smem + L::kXOff + xs * L::kXBytes);
-            for (int pp = 0; pp < P; ++pp) {
-                const int s = pp & 1;
-                HP_WAIT(HP_MMA_ACC1_EMPTY, mbar_wait_sel(&acc1_empty[s], ((s ? use1 : use0) & 1) ^ 1, p.park & 2u));
-                tcgen05_fence_after();
-                const uint32_t d1 = tmem_base + (uint32_t)(s * 128);
-#pragma unroll
-                for (int kc = 0; kc < 2; ++kc) {
-                    HP_WAIT(HP_MMA_W1, mbar_wait_sel(&w1_full[w1s], w1ph, p.park & 2u));
+            int w2s = 0;
+            uint32_t w2ph = 0;
+            uint32_t useb0 = 0, useb1 = 0;     // uses of A2 buffer 0 / 1
+            int local_tile = 0;
+            for (int u = unit0; u < num_units; u += unit_step, ++local_tile) {
+                const int st = local_tile & 1;                 // acc2 stage: the previous tile's outputs drain meanwhile
+                for (int pp = 0; pp < P; ++pp) {
+                    const int buf = pp & 1;
+                    HP_WAIT(HP_MMA_A2_FULL, mbar_wait_sel(&a2_full[buf], (buf ? useb1 : useb0) & 1, p.park & 2u));
+                    if (pp == 0)
+                        HP_WAIT(HP_MMA_ACC2_EMPTY, mbar_wait_sel(&acc2_empty[st], (uint32_t)(((local_tile >> 1) & 1) ^ 1), p.park & 2u));
+                    HP_WAIT(HP_MMA_W2, mbar_wait_sel(&w2_full[w2s], w2ph, p.park & 2u));
                     tcgen05_fence_after();
+                    const bool is_a = pp < half;
+                    const int kslice = is_a ? pp : pp - half;
+                    const uint32_t d = tmem_base + kAcc2Col + (uint32_t)st * kAcc2Stride + (is_a ? 0u : kAcc2OffB);
+                    const uint32_t w2 = smem_u32(smem + L::kW2Off + w2s * L::kW2Bytes);
                     if (elect_one()) {
-                        const uint64_t da = make_kmajor_desc<128>(xa + kc * 16384);
-                        const uint64_t db = make_kmajor_desc<128>(smem_u32(smem + L::kW1Off + w1s * L::kW1Bytes));
+                        // A operand = the hidden activations the epilogue wrote back to tensor memory (no shared-memory round trip)
+                        const uint32_t a2t = tmem_base + kA2TmemCol + (uint32_t)(buf * 64);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if constexpr (PAIR)
-                                umma_bf16_ss_2sm(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
-                            else
-                                umma_bf16_ss(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc1, (kc | k) != 0 ? 1u : 0u);
+                        for (int kc = 0; kc < 2; ++kc) {
+                            const uint64_t db = make_kmajor_desc<128>(w2 + kc * 4096);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if constexpr (PAIR)
+                                    umma_bf16_ts_2sm(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2),
+                                                     is_a ? kIdescA : kIdescB, (kslice | kc | k) != 0 ? 1u : 0u);
+                                else
+                                    umma_bf16_ts(d, a2t + (uint32_t)((kc * 4 + k) * 8), db + (uint64_t)(k * 2),
+                                                 is_a ? kIdescA : kIdescB, (kslice | kc | k) != 0 ? 1u : 0u);
+                            }
                         }
-                        commit(&w1_empty[w1s]);
-                        if (kc == 1) {
-                            commit(&acc1_full[s]);
-                            if (pp == P - 1) commit(&x_empty[xs]);
-                        }
+                        commit(&a2_empty[buf]);
+                        commit(&w2_empty[w2s]);
+                        if (pp == P - 1) commit(&acc2_full[st]);
                     }
                     __syncwarp();
-                    if (++w1s == kW1Stages) { w1s = 0; w1ph ^= 1; }
+                    if (buf) ++useb1; else ++useb0;
+                    if (++w2s == kW2Stages) { w2s = 0; w2ph ^= 1; }
                 }
-                if (s) ++use1; else ++use0;
-                if (++issued1 >= 3) mma2();
             }
-            if (++xs == kXStages) { xs = 0; xph ^= 1; }
         }
-        while (m2_tile < local_tile) mma2();     // the two (or fewer) passes still in flight
-        }
-    } else if (warp >= kHpEpiWarp0) {
+    } else if (warp >= kHpEpiWarp0 && warp < kHpEpiWarp0 + 8) {
         // ===================== epilogue groups =====================
         const int q = (warp - kHpEpiWarp0) & 3;               // TMEM lane quarter == warp % 4
         const int grp = (warp - kHpEpiWarp0) >> 2;            // owns acc1 stage / A2 buffer `grp`
@@ -433,7 +439,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         if (grp == 0 && prev_tile >= 0) epilogue2(local_tile - 1, prev_tile);
     }
-    if (p.prof && lane == 0 && (warp == 1 || warp == kHpEpiWarp0)) {
+    if (p.prof && lane == 0 && (warp == 1 || warp == kHpMma2Warp || warp == kHpEpiWarp0)) {
         if (warp == 1) hp_acc[HP_TOTAL] = (unsigned long long)(clock64() - hp_start);
 #pragma unroll
         for (int i = 0; i < HP_N; ++i)
@@ -484,7 +490,7 @@ HeadPairPlan *head_pair_plan_create(const HeadPairDesc &d, char *err, size_t err
     pl->grid = p.num_m_tiles < sms ? p.num_m_tiles : sms;
     {
         static const char *pe = getenv("LWOP_HEADS_PAIR");
-        pl->pair = ((pe ? atoi(pe) != 0 : true) && p.num_m_tiles >= 4) ? 1 : 0;
+        pl->pair = ((pe ? atoi(pe) != 0 : false) && p.num_m_tiles >= 4) ? 1 : 0;   // opt-in: measured 2-5 % slower than the single-CTA form
         if (pl->pair) {
             const int units = (p.num_m_tiles + 1) / 2;
             pl->grid = 2 * (units < sms / 2 ? units : sms / 2);
