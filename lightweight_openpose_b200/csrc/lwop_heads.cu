@@ -374,10 +374,28 @@ head_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
                 if (p.cat) {
                     __nv_bfloat16 *o = p.cat + m * p.ldc;
+                    if (p.cat_col_a == 0 && p.cat_col_b == 14 && (p.ldc & 7) == 0) {
+                        // the concat layout of lightweight_openpose.py:36 (heat 0..13, paf 14..39): 80 contiguous bytes per
+                        // row = five 128-bit stores instead of forty 16-bit ones
+                        float v[40];
 #pragma unroll
-                    for (int j = 0; j < 14; ++j) o[p.cat_col_a + j] = __float2bfloat16_rn(va[j]);
+                        for (int j = 0; j < 14; ++j) v[j] = va[j];
 #pragma unroll
-                    for (int j = 0; j < 26; ++j) o[p.cat_col_b + j] = __float2bfloat16_rn(vb[j]);
+                        for (int j = 0; j < 26; ++j) v[14 + j] = vb[j];
+                        uint4 *o4 = reinterpret_cast<uint4 *>(o);
+#pragma unroll
+                        for (int q4 = 0; q4 < 5; ++q4) {
+                            uint4 w;
+                            w.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]); w.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+                            w.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); w.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+                            o4[q4] = w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 14; ++j) o[p.cat_col_a + j] = __float2bfloat16_rn(va[j]);
+#pragma unroll
+                        for (int j = 0; j < 26; ++j) o[p.cat_col_b + j] = __float2bfloat16_rn(vb[j]);
+                    }
                 }
             }
             if (p.prof) hp_acc[HP_E2_WORK] += (unsigned long long)(clock64() - hp_e2);
