@@ -5,13 +5,21 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this module; the product package
 ``lightweight_openpose_b200`` never does.
 
-PARITY UNPINNED for the forward: the reference graph
+PARITY of the forward: the reference graph
 (``/root/reference/src/lightweight_openpose.py:8-48`` built from
 ``/root/reference/src/net_factory.py:4-37``) needs TensorFlow 1.x, which is not
 installed and cannot be installed (no network), and the reference ships no
 golden activations.  This file restates that graph with torch-CPU ``F.conv2d``
-under the TF semantics below; the decode half of the path *is* pinned (see
-``oracle/decode_oracle.py``).
+under the TF semantics below.
+* WIRING PINNED: ``tests/test_oracle_forward.py`` executes the UNMODIFIED reference model
+  function on a stand-in for the handful of TensorFlow calls it makes (``tests/tf_shim.py``) and
+  this oracle agrees with it to 1e-5 -- layer order, widths, strides, dilations, where BN /
+  ReLU / ELU / bias sit, the ``tf.add`` / ``tf.concat`` edges and the creation order (= names) of
+  all 173 inference variables come from the reference source itself.
+* OP ARITHMETIC UNPINNED: what each TensorFlow op computes ('same' padding, separable =
+  depthwise then pointwise, BN epsilon) is restated from TensorFlow's documentation in both
+  the shim and this file; no TensorFlow binary was available to confirm it.
+The decode half of the path is pinned bit for bit (see ``oracle/decode_oracle.py``).
 
 TF semantics restated here
 * tensors NHWC, kernels HWIO, cross-correlation;
