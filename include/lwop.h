@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LWOP_ABI_VERSION 1
+#define LWOP_ABI_VERSION 2
 
 /* error codes */
 #define LWOP_OK                 0
@@ -68,13 +68,15 @@ extern "C" {
 #define LWOP_STRIDE        8
 
 /* decode table capacities (per image) */
-#define LWOP_MAX_PEAKS    128      /* peaks per joint channel */
-#define LWOP_MAX_JOINTS  1792      /* 14 * 128 rows of the joint list */
-#define LWOP_MAX_PERSONS  128
+#define LWOP_MAX_PEAKS    256      /* peaks per joint channel: above the geometric maximum of the radius-5 search on
+                                      maps up to ~4400 pixels (46 x 82: ~175), so BASELINE's frame sizes cannot overflow */
+#define LWOP_MAX_JOINTS  3584      /* 14 * 256 rows of the joint list */
+#define LWOP_MAX_PERSONS  256
 #define LWOP_COUNTS        32      /* int32 slots per image, see below */
 /* counts[b][0] = rows in the joint list, [1] = persons, [2] = overflow bitmask
- * (1: peaks/channel, 2: persons, 4: candidates), [3] = total connections,
- * [4..17] = peaks per joint channel, [18..30] = connections per limb type */
+ * (1: peaks/channel, 2: persons), [3] = total connections,
+ * [4..17] = peaks per joint channel, [18..30] = connections per limb type,
+ * [31] = internal (image handed from the register-resident grouping kernel to the general one) */
 
 typedef struct lwop_handle lwop_handle;
 
@@ -137,6 +139,14 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
                 int map_h, int map_w, int img_h, int img_w, float thre1, double thre2,
                 const lwop_decode_tables *tables_dev, void *stream);
 
+/* lwop_forward (or lwop_forward_u8 when is_u8) followed by lwop_decode of its maps as ONE stream operation: in bf16
+ * mode the forward kernels and the decode chain are replayed from a single CUDA graph, the decode kernels chained to
+ * the last head kernel with programmatic dependent launches (what the per-frame loop body of
+ * test&eval/model_test.py:68,71 does, batched, without leaving the device).  Maps in heat_dev / paf_dev, results in
+ * tables_dev; image size = the handle's (H, W). */
+int lwop_forward_decode(lwop_handle *h, const void *in_dev, int is_u8, int batch, int mode, float thre1, double thre2,
+                        float *heat_dev, float *paf_dev, const lwop_decode_tables *tables_dev, void *stream);
+
 /* ---- the decode stages, separately callable (what src/pose_decode.py also exports) ----
  * Peak table layout shared by the three calls (device memory, caller-allocated):
  *   peaks        float [batch][14][LWOP_MAX_PEAKS][4]   (x, y, score, unused) per joint channel, in kept order
@@ -156,10 +166,13 @@ int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int ma
 /* find_connected_joints (pose_decode.py:188-301).  paf_dev is either the network's PAF map [batch][h][w][26]
  * (paf_upsampled = 0: the bicubic up-sampling of decode_pose :487 is evaluated on the fly) or an already
  * up-sampled [batch][H][W][26] map (paf_upsampled = 1, what the reference function is handed).
+ * num_intermed_pts (1..64) and max_dist_thresh are the reference's keyword arguments of the same names
+ * (defaults 10 and 1; lwop_decode uses the defaults, as decode_pose does).
  * Writes limbs_dev [batch][13][LWOP_MAX_PEAKS][5] and counts_dev[b][18 + limb_type]. */
 int lwop_find_connected_joints(lwop_handle *h, const float *paf_dev, int paf_upsampled, int batch, int map_h, int map_w,
-                               int img_h, int img_w, double thre2, const float *peaks_dev,
-                               const int32_t *peak_counts_dev, double *limbs_dev, int32_t *counts_dev, void *stream);
+                               int img_h, int img_w, double thre2, int num_intermed_pts, double max_dist_thresh,
+                               const float *peaks_dev, const int32_t *peak_counts_dev, double *limbs_dev,
+                               int32_t *counts_dev, void *stream);
 
 /* joint list + group_limbs_of_same_person + keypoint table (pose_decode.py:481-482, :304-396, :403-429):
  * fills joints / persons / keypoints of `tables_dev` and counts[b][0], [1], [3] from the peak and limb tables. */

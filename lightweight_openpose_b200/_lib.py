@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "_lwop.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lwop.h")
 
 # constants mirrored from include/lwop.h
+ABI_VERSION = 2
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_WEIGHTS, ERR_OVERFLOW, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 MODE_BF16, MODE_FP32_CHECK, MODE_BF16_DIRECT = 0, 1, 2
@@ -26,7 +27,7 @@ FLAG_NO_FUSE_SEP = 2
 FLAG_NO_FUSE_HEADS = 4
 PEAKS_NO_REFINE, PEAKS_CROSS, PEAKS_GAUSS = 1, 2, 4
 NUM_JOINTS, NUM_PAFS, NUM_LIMBS = 14, 26, 13
-MAX_PEAKS, MAX_JOINTS, MAX_PERSONS, COUNTS = 128, 1792, 128, 32
+MAX_PEAKS, MAX_JOINTS, MAX_PERSONS, COUNTS = 256, 3584, 256, 32
 
 
 class LwopError(RuntimeError):
@@ -61,8 +62,9 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_forward_u8": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "lwop_preprocess_bgr_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "lwop_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _d, C.POINTER(DecodeTables), _vp]),
+    "lwop_forward_decode": (_i, [_vp, _vp, _i, _i, _i, _f, _d, _vp, _vp, C.POINTER(DecodeTables), _vp]),
     "lwop_nms": (_i, [_vp, _vp, _i, _i, _i, _d, _f, _i, _vp, _vp, _vp, _vp]),
-    "lwop_find_connected_joints": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "lwop_find_connected_joints": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "lwop_group_limbs": (_i, [_vp, _vp, _vp, _i, C.POINTER(DecodeTables), _vp]),
     "lwop_decode_fetch": (_i, [_vp, C.POINTER(DecodeTables), _i, C.POINTER(PackedTables), _vp]),
     "lwop_infer_host": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp]),
@@ -112,7 +114,7 @@ def load():
         except AttributeError as exc:
             raise ImportError(f"{LIB_PATH} does not export {name}") from exc
         fn.restype, fn.argtypes = SIGNATURES[name]
-    if lib.lwop_abi_version() != 1:
+    if lib.lwop_abi_version() != ABI_VERSION:
         raise ImportError("lwop ABI version mismatch")
     _lib = lib
     return lib

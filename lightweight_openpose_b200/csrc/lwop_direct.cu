@@ -256,25 +256,22 @@ cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s) {
 // weights broadcast from shared memory; the output row (64 B) is written with
 // four 128-bit stores.
 // ---------------------------------------------------------------------------
-// Folded weights [27][32] (k = tap*3 + c major) and bias of the first conv live in constant
-// memory: with the 27 x 32 loop fully unrolled every FFMA takes its weight straight from
-// the constant bank (no shared-memory or register traffic for the 864 taps).
-__constant__ float c_conv1_w[27 * 32];
-__constant__ float c_conv1_b[32];
-// uint8 -> float32(u8 / 255.0) table (the reference's `img / 255.` in float64, fed as float32), filled by the host
+// Folded weights [27][32] (k = tap*3 + c major) and bias of the first conv travel as a by-value kernel parameter
+// (Conv1Weights, 3.5 KB): kernel parameters live in the constant bank, so with the 27 x 32 loop fully unrolled
+// every FFMA takes its weight straight from there (no shared-memory or register traffic for the 864 taps) -- and,
+// unlike a __constant__ symbol, they belong to the handle that launches: two handles with different checkpoints on
+// one device do not share layer 0.
+// uint8 -> float32(u8 / 255.0) table (the reference's `img / 255.` in float64, fed as float32), filled by the host;
+// the same 256 values for every handle
 __device__ float g_u8_lut[256];
 
-cudaError_t set_conv1_constants(const float *w_host_n27 /*[32][27]*/, const float *b_host /*[32]*/) {
-    float t[27 * 32];
+cudaError_t conv1_pack_weights(const float *w_host_n27 /*[32][27]*/, const float *b_host /*[32]*/, Conv1Weights *out) {
     for (int n = 0; n < 32; ++n)
-        for (int k = 0; k < 27; ++k) t[k * 32 + n] = w_host_n27[n * 27 + k];
-    cudaError_t e = cudaMemcpyToSymbol(c_conv1_w, t, sizeof(t));
-    if (e != cudaSuccess) return e;
+        for (int k = 0; k < 27; ++k) out->w[k * 32 + n] = w_host_n27[n * 27 + k];
+    for (int n = 0; n < 32; ++n) out->b[n] = b_host[n];
     float lut[256];
     for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);
-    e = cudaMemcpyToSymbol(g_u8_lut, lut, sizeof(lut));
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_conv1_b, b_host, 32 * sizeof(float));
+    return cudaMemcpyToSymbol(g_u8_lut, lut, sizeof(lut));
 }
 
 // Two horizontally adjacent output pixels per thread: every 128-bit weight load from the constant bank feeds both,
@@ -282,8 +279,8 @@ cudaError_t set_conv1_constants(const float *w_host_n27 /*[32][27]*/, const floa
 // pair, accumulator pair = two adjacent output channels).  Each output keeps its 27-step accumulation order.
 template <typename TIn>
 __global__ void __launch_bounds__(128)
-conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, int H, int W, int Ho, int Wo,
-                  int pad_t, int pad_l) {
+conv1_bf16_kernel(const __grid_constant__ Conv1Weights cw, const TIn *__restrict__ in, uint4 *__restrict__ out, int B, int H,
+                  int W, int Ho, int Wo, int pad_t, int pad_l) {
     __shared__ float lut[256];
     if (sizeof(TIn) == 1) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_u8_lut[i];
@@ -302,7 +299,7 @@ conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, in
     const bool two = ox + 1 < Wo;
     float2 acc[2][16];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = make_float2(c_conv1_b[2 * n], c_conv1_b[2 * n + 1]);
+    for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = make_float2(cw.b[2 * n], cw.b[2 * n + 1]);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
         const int iy = oy * 2 - pad_t + dy;
@@ -327,7 +324,7 @@ conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, in
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float2 v0 = make_float2(v[dx][c], v[dx][c]), v1 = make_float2(v[dx + 2][c], v[dx + 2][c]);
-                const float *wr = c_conv1_w + ((dy * 3 + dx) * 3 + c) * 32;
+                const float *wr = cw.w + ((dy * 3 + dx) * 3 + c) * 32;
 #pragma unroll
                 for (int n = 0; n < 16; ++n) {
                     const float2 w2 = make_float2(wr[2 * n], wr[2 * n + 1]);
@@ -352,15 +349,16 @@ conv1_bf16_kernel(const TIn *__restrict__ in, uint4 *__restrict__ out, int B, in
     }
 }
 
-cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s) {
+cudaError_t launch_conv1_bf16(const Conv1Weights &cw, const void *in, int in_is_u8, void *out, int B, int H, int W,
+                              cudaStream_t s) {
     SamePad ph = same_pad(H, 3, 2, 1), pw = same_pad(W, 3, 2, 1);
     long long total = (long long)B * ph.out * ((pw.out + 1) / 2);      // one thread per pair of output pixels
     unsigned grid = (unsigned)((total + 127) / 128);
     if (in_is_u8)
-        return launch_chain(conv1_bf16_kernel<uint8_t>, grid, 128, 0, s, 1, (const uint8_t *)in, (uint4 *)out, B, H, W, ph.out,
-                            pw.out, ph.before, pw.before);
-    return launch_chain(conv1_bf16_kernel<float>, grid, 128, 0, s, 1, (const float *)in, (uint4 *)out, B, H, W, ph.out, pw.out,
-                        ph.before, pw.before);
+        return launch_chain(conv1_bf16_kernel<uint8_t>, grid, 128, 0, s, 1, cw, (const uint8_t *)in, (uint4 *)out, B, H, W,
+                            ph.out, pw.out, ph.before, pw.before);
+    return launch_chain(conv1_bf16_kernel<float>, grid, 128, 0, s, 1, cw, (const float *)in, (uint4 *)out, B, H, W, ph.out,
+                        pw.out, ph.before, pw.before);
 }
 
 // uint8 frame -> float32 / 255 (reference test&eval/model_test.py:65 `img_data / 255.`:

@@ -31,12 +31,14 @@ struct DwArgs {
 cudaError_t launch_conv_direct(const ConvArgs &a, cudaStream_t s);
 cudaError_t launch_depthwise_simple(const DwArgs &a, cudaStream_t s);
 cudaError_t launch_depthwise_bf16(const DwArgs &a, cudaStream_t s);
-cudaError_t set_conv1_constants(const float *w_host_n27, const float *b_host);   // per device, at weight load
-cudaError_t launch_conv1_bf16(const void *in, int in_is_u8, void *out, int B, int H, int W, cudaStream_t s);
-// lwop_conv1.cu -- the first layer as a tcgen05 implicit GEMM (im2col rows assembled by producer warps)
-void conv1_tc_pack_weights(const float *w_n27, uint16_t *w_u8_32x32, uint16_t *w_f32_32x64);
-cudaError_t launch_conv1_tc(const void *in, int in_is_u8, void *out, const void *w_u8_dev, const void *w_f32_dev,
-                            const float *bias_dev, int B, int H, int W, cudaStream_t s);
+// first conv (3 -> 32, stride 2): folded taps [27][32] + bias, passed to the kernel by value (per handle)
+struct Conv1Weights {
+    float w[27 * 32];
+    float b[32];
+};
+cudaError_t conv1_pack_weights(const float *w_host_n27, const float *b_host, Conv1Weights *out);   // at weight load
+cudaError_t launch_conv1_bf16(const Conv1Weights &cw, const void *in, int in_is_u8, void *out, int B, int H, int W,
+                              cudaStream_t s);
 cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStream_t s);
 cudaError_t launch_preprocess_bgr(const uint8_t *in, int B, int Hs, int Ws, uint8_t *out, int H, int W, cudaStream_t s);
 cudaError_t launch_pack_bf16(const float *src, void *dst, long long rows, int cols, int cols_padded,
@@ -69,11 +71,11 @@ bool gemm_driver_ready(char *err, size_t errlen);
 // launch with the programmatic-dependent-launch attribute (unless LWOP_PDL=0) and an optional cluster width
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(void (*kfn)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, int cluster_x,
+inline cudaError_t launch_chain(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
                                 Args &&...args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -166,7 +168,8 @@ size_t decode_scratch_peaks_bytes(int B);
 cudaError_t launch_decode_peaks(const float *heat, int B, int h, int w, double factor, float thre1, int mode,
                                 float *peaks, int *peak_counts, int *counts, cudaStream_t s);
 cudaError_t launch_decode_limbs(const float *paf, int upsampled, int B, int h, int w, int H, int W, double thre2,
-                                const float *peaks, const int *peak_counts, double *limbs, int *counts, cudaStream_t s);
+                                int num_intermed_pts, double max_dist_thresh, const float *peaks, const int *peak_counts,
+                                double *limbs, int *counts, cudaStream_t s);
 cudaError_t launch_decode_group(const float *peaks, const int *peak_counts, const double *limbs, int *counts,
                                 double *joints, double *persons, float *keypoints, double *work, int B, cudaStream_t s);
 size_t decode_scratch_work_bytes(int B);

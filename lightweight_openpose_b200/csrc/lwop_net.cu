@@ -98,6 +98,10 @@ struct GraphEntry {
     void *heat = nullptr, *paf = nullptr, *h1 = nullptr, *p1 = nullptr;
     int in_u8 = 0;
     int launches = 0;
+    // decode chain captured behind the forward (lwop_forward_decode): its tables and thresholds
+    void *dec_counts = nullptr;
+    float thre1 = 0.f;
+    double thre2 = 0.0;
 };
 
 }  // namespace
@@ -116,8 +120,7 @@ struct lwop_handle {
     void *w_bf16[kNumLayers] = {};               // [Cout_pad][taps][Cin_pad] bf16
     float *b_pad[kNumLayers] = {};               // [Cout_pad] fp32
     float *w_f32pad[kNumLayers] = {};            // fp32 weights with padded Cin (only layer 24: 40 -> 64)
-    void *c1_w_u8 = nullptr, *c1_w_f32 = nullptr;   // first layer, tensor-core operand tables (lwop_conv1.cu)
-    float *c1_bias = nullptr;
+    Conv1Weights c1 = {};                        // first layer: folded taps + bias, a by-value kernel parameter
 
     // program + arenas
     std::vector<Step> steps;
@@ -442,6 +445,7 @@ struct FwdIO {
     const void *in;
     int in_u8;
     float *heat, *paf, *h1, *p1;
+    const DecodeArgs *dec = nullptr;     // decode chain to run behind the forward (same stream / same graph), or nullptr
 };
 
 // Issue every kernel of one forward pass on `s`.  With `ev` (2 events per step)
@@ -479,15 +483,8 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
         const void *in = st.in == B_IN ? (const void *)in_f32 : arena[st.in];
         float *out2 = st.out2 == B_H1 ? io.h1 : st.out2 == B_P1 ? io.p1 : nullptr;
         if (st.layer == 0) {
-            // The tensor-core variant of this layer (lwop_conv1.cu) is correct but measured SLOWER than the fp32-FMA
-            // kernel on B200 (1.05 ms vs 0.39 ms per 256 frames: 128x32x32 MMAs are too small to amortise the
-            // per-tile barrier round trips of a one-CTA-per-SM pipeline); it stays opt-in: LWOP_CONV1_TC=1.
-            static const bool c1_tc = getenv("LWOP_CONV1_TC") != nullptr;
-            if (mode == LWOP_MODE_BF16 && c1_tc) {
-                CU_OK(h, launch_conv1_tc(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, h->c1_w_u8, h->c1_w_f32,
-                                         h->c1_bias, batch, st.H, st.W, s));
-            } else if (!f32) {
-                CU_OK(h, launch_conv1_bf16(io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, batch, st.H, st.W, s));
+            if (!f32) {
+                CU_OK(h, launch_conv1_bf16(h->c1, io.in_u8 ? io.in : (const void *)in_f32, io.in_u8, out, batch, st.H, st.W, s));
             } else {
                 ConvArgs a{};
                 a.in = in_f32; a.in_dtype = LWOP_DT_F32; a.w = h->blob + h->off_w[0]; a.bias = h->blob + h->off_b[0];
@@ -545,6 +542,11 @@ int run_forward(lwop_handle *h, int batch, int mode, const FwdIO &io, cudaStream
             h->launches++;
         }
     }
+    if (io.dec) {       // the decode chain follows the last head kernel with programmatic dependent launches
+        DecodeArgs a = *io.dec;
+        a.heat = io.heat; a.paf = io.paf; a.B = batch; a.h = h->h8; a.w = h->w8; a.H = h->H; a.W = h->W;
+        CU_OK(h, launch_decode(a, s, &h->launches));
+    }
     return LWOP_OK;
 }
 
@@ -566,7 +568,8 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
     GraphEntry *gp = nullptr;
     for (auto &c : cache)
         if (c.exec && c.in == io.in && c.heat == io.heat && c.paf == io.paf && c.h1 == io.h1 && c.p1 == io.p1 &&
-            c.in_u8 == io.in_u8) {
+            c.in_u8 == io.in_u8 && c.dec_counts == (io.dec ? (void *)io.dec->t.counts : nullptr) &&
+            (!io.dec || (c.thre1 == io.dec->thre1 && c.thre2 == io.dec->thre2))) {
             gp = &c;
             break;
         }
@@ -604,6 +607,7 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
         cudaStreamDestroy(cs);
         if (e != cudaSuccess) return fail(h, LWOP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
         ne.in = io.in; ne.heat = io.heat; ne.paf = io.paf; ne.h1 = io.h1; ne.p1 = io.p1; ne.in_u8 = io.in_u8;
+        if (io.dec) { ne.dec_counts = io.dec->t.counts; ne.thre1 = io.dec->thre1; ne.thre2 = io.dec->thre2; }
         ne.launches = launches_per_forward;
         cache.push_back(ne);
         gp = &cache.back();
@@ -746,9 +750,6 @@ int lwop_destroy(lwop_handle *h) {
         if (h->b_pad[i]) cudaFree(h->b_pad[i]);
         if (h->w_f32pad[i]) cudaFree(h->w_f32pad[i]);
     }
-    if (h->c1_w_u8) cudaFree(h->c1_w_u8);
-    if (h->c1_w_f32) cudaFree(h->c1_w_f32);
-    if (h->c1_bias) cudaFree(h->c1_bias);
     if (h->blob) cudaFree(h->blob);
     if (h->peaks) cudaFree(h->peaks);
     if (h->peak_counts) cudaFree(h->peak_counts);
@@ -815,18 +816,8 @@ int lwop_load_weights(lwop_handle *h, const float *host_blob, size_t num_floats)
         h->off_b[i] = off;
         off += l.cout;
     }
-    // first conv: taps in constant memory (one process drives one GPU, so the per-device symbol is unambiguous)
-    CU_OK(h, set_conv1_constants(host_blob + h->off_w[0], host_blob + h->off_b[0]));
-    {   // the same layer as tensor-core operand tables (default first-layer kernel in bf16 mode)
-        uint16_t w8[32 * 32], wf[32 * 64];
-        conv1_tc_pack_weights(host_blob + h->off_w[0], w8, wf);
-        if (!h->c1_w_u8) CU_OK(h, cudaMalloc(&h->c1_w_u8, sizeof(w8)));
-        if (!h->c1_w_f32) CU_OK(h, cudaMalloc(&h->c1_w_f32, sizeof(wf)));
-        if (!h->c1_bias) CU_OK(h, cudaMalloc(&h->c1_bias, 32 * sizeof(float)));
-        CU_OK(h, cudaMemcpy(h->c1_w_u8, w8, sizeof(w8), cudaMemcpyHostToDevice));
-        CU_OK(h, cudaMemcpy(h->c1_w_f32, wf, sizeof(wf), cudaMemcpyHostToDevice));
-        CU_OK(h, cudaMemcpy(h->c1_bias, host_blob + h->off_b[0], 32 * sizeof(float), cudaMemcpyHostToDevice));
-    }
+    // first conv: taps + bias packed for the by-value kernel parameter (per handle)
+    CU_OK(h, conv1_pack_weights(host_blob + h->off_w[0], host_blob + h->off_b[0], &h->c1));
     // bf16 operand layouts for the tensor-core path: [Cout_pad][taps][Cin_pad], bias [Cout_pad]
     for (int i = 1; i < kNumLayers; ++i) {
         const LayerSpec &l = kLayers[i];
@@ -890,6 +881,20 @@ int lwop_decode(lwop_handle *h, const float *heat_dev, const float *paf_dev, int
     return LWOP_OK;
 }
 
+int lwop_forward_decode(lwop_handle *h, const void *in_dev, int is_u8, int batch, int mode, float thre1, double thre2,
+                        float *heat_dev, float *paf_dev, const lwop_decode_tables *t, void *stream) {
+    if (!h || !t || !t->counts || !t->joints || !t->limbs || !t->persons || !t->keypoints)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if ((long long)h->h8 * h->w8 > 16384) return fail(h, LWOP_ERR_UNSUPPORTED, "heat map larger than 16384 pixels");
+    CU_OK(h, cudaSetDevice(h->device));
+    int rc = ensure_decode_scratch(h);
+    if (rc != LWOP_OK) return rc;
+    DecodeArgs a{};
+    a.thre1 = thre1; a.thre2 = thre2; a.t = *t; a.peaks = h->peaks; a.peak_counts = h->peak_counts; a.work = h->group_work;
+    FwdIO io{in_dev, is_u8, heat_dev, paf_dev, nullptr, nullptr, &a};
+    return forward_impl(h, io, batch, mode, (cudaStream_t)stream);
+}
+
 int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int map_w, double factor, float thre1,
              int mode, float *peaks_dev, int32_t *peak_counts_dev, int32_t *counts_dev, void *stream) {
     if (!h || !heat_dev || !peaks_dev || !peak_counts_dev || !counts_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
@@ -903,18 +908,22 @@ int lwop_nms(lwop_handle *h, const float *heat_dev, int batch, int map_h, int ma
     CU_OK(h, cudaSetDevice(h->device));
     CU_OK(h, launch_decode_peaks(heat_dev, batch, map_h, map_w, factor, thre1, mode, peaks_dev, peak_counts_dev,
                                  counts_dev, (cudaStream_t)stream));
-    h->launches += 2;
+    h->launches += 3;
     return LWOP_OK;
 }
 
 int lwop_find_connected_joints(lwop_handle *h, const float *paf_dev, int paf_upsampled, int batch, int map_h, int map_w,
-                               int img_h, int img_w, double thre2, const float *peaks_dev,
-                               const int32_t *peak_counts_dev, double *limbs_dev, int32_t *counts_dev, void *stream) {
+                               int img_h, int img_w, double thre2, int num_intermed_pts, double max_dist_thresh,
+                               const float *peaks_dev, const int32_t *peak_counts_dev, double *limbs_dev,
+                               int32_t *counts_dev, void *stream) {
     if (!h || !paf_dev || !peaks_dev || !peak_counts_dev || !limbs_dev || !counts_dev)
         return fail(h, LWOP_ERR_INVALID, "null argument");
     if (batch < 1 || map_h < 1 || map_w < 1 || img_h < 1 || img_w < 1) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    if (num_intermed_pts < 1 || num_intermed_pts > 64)
+        return fail(h, LWOP_ERR_UNSUPPORTED, "num_intermed_pts must be in 1..64");
     CU_OK(h, cudaSetDevice(h->device));
-    CU_OK(h, launch_decode_limbs(paf_dev, paf_upsampled, batch, map_h, map_w, img_h, img_w, thre2, peaks_dev,
+    CU_OK(h, launch_decode_limbs(paf_dev, paf_upsampled, batch, map_h, map_w, img_h, img_w, thre2, num_intermed_pts,
+                                 max_dist_thresh, peaks_dev,
                                  peak_counts_dev, limbs_dev, counts_dev, (cudaStream_t)stream));
     h->launches++;
     return LWOP_OK;
@@ -930,7 +939,7 @@ int lwop_group_limbs(lwop_handle *h, const float *peaks_dev, const int32_t *peak
     if (rc != LWOP_OK) return rc;
     CU_OK(h, launch_decode_group(peaks_dev, peak_counts_dev, t->limbs, t->counts, t->joints, t->persons, t->keypoints,
                                  h->group_work, batch, (cudaStream_t)stream));
-    h->launches++;
+    h->launches += 2;
     return LWOP_OK;
 }
 
@@ -1085,11 +1094,8 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
                                  (size_t)nb * img_elems * esz, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
         CU_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
-        FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr};
-        rc = forward_impl(h, io, nb, mode, s);
-        if (rc != LWOP_OK) return rc;
-        CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
-        CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
+        // forward + decode chain: ONE graph launch on `s` (the decode kernels follow the last head kernel with
+        // programmatic dependent launches); compaction and the downloads run on the decode stream behind it
         lwop_decode_tables t = ln.tables;
         t.counts += (size_t)b0 * LWOP_COUNTS;
         t.joints += (size_t)b0 * LWOP_MAX_JOINTS * 6;
@@ -1097,12 +1103,15 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
         t.persons += (size_t)b0 * LWOP_MAX_PERSONS * 16;
         t.keypoints += (size_t)b0 * LWOP_MAX_PERSONS * 42;
         DecodeArgs a{};
-        a.heat = h->slot_heat[slot]; a.paf = h->slot_paf[slot]; a.B = nb; a.h = h->h8; a.w = h->w8; a.H = h->H; a.W = h->W;
         a.thre1 = thre1; a.thre2 = thre2; a.t = t;
         a.peaks = h->peaks + (size_t)b0 * LWOP_NUM_JOINTS * LWOP_MAX_PEAKS * 4;
         a.peak_counts = h->peak_counts + (size_t)b0 * 16;
         a.work = h->group_work + (size_t)b0 * LWOP_NUM_LIMBS * LWOP_MAX_PEAKS * 16;
-        CU_OK(h, launch_decode(a, ds, &h->launches));
+        FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr, &a};
+        rc = forward_impl(h, io, nb, mode, s);
+        if (rc != LWOP_OK) return rc;
+        CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
+        CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
         if (heat_host)
             CU_OK(h, cudaMemcpyAsync(heat_host + (size_t)b0 * px * LWOP_NUM_JOINTS, h->slot_heat[slot],
                                      (size_t)nb * px * LWOP_NUM_JOINTS * 4, cudaMemcpyDeviceToHost, ds));

@@ -34,6 +34,32 @@ def require_gpu(device: int = 0) -> None:
         raise _lib.LwopError(_lib.ERR_NO_DEVICE, "lwop kernels are built for sm_100a (B200) only")
 
 
+def validate_host_images(images_host, height: int, width: int, max_batch: int):
+    """Host frames for the whole-path calls -> contiguous CPU tensor ``[B, H, W, 3]`` uint8 or float32.
+    The C side reads ``B*H*W*3`` elements of the stated type from a raw pointer, so everything is checked here:
+    shape against the engine, batch against its capacity, contiguity, dtype.  float64 / float16 frames (the
+    reference's own ``img / 255.`` is float64, ``test&eval/model_test.py:65``) are cast to float32, which is what
+    the reference's float32 placeholder does to its feed; any other dtype raises."""
+    torch = _torch()
+    if isinstance(images_host, np.ndarray):
+        images_host = torch.from_numpy(np.ascontiguousarray(images_host))
+    if not isinstance(images_host, torch.Tensor):
+        raise ValueError("images_host must be a numpy array or a CPU torch tensor")
+    if images_host.device.type != "cpu":
+        raise ValueError("images_host must live in host memory (use forward() for CUDA tensors)")
+    if images_host.dim() != 4 or tuple(images_host.shape[1:]) != (height, width, 3):
+        raise ValueError(f"engine built for frames [B,{height},{width},3], got {tuple(images_host.shape)}")
+    if not 1 <= images_host.shape[0] <= max_batch:
+        raise ValueError(f"batch {images_host.shape[0]} outside 1..{max_batch}")
+    if images_host.dtype in (torch.float64, torch.float16, torch.bfloat16):
+        images_host = images_host.to(torch.float32)
+    elif images_host.dtype not in (torch.uint8, torch.float32):
+        raise ValueError(f"frames must be uint8 or floating point, got {images_host.dtype}")
+    if not images_host.is_contiguous():
+        images_host = images_host.contiguous()
+    return images_host
+
+
 class DecodeResult:
     """Per-image decode output in the reference's types (pose_decode.py:516-517)."""
     __slots__ = ("joint_list", "person_to_joint_assoc", "joints", "limbs", "counts")
@@ -268,6 +294,25 @@ class Engine:
                                         float(np.float32(thre1)), float(thre2), C.byref(s), self._stream()),
                    self.handle)
 
+    def forward_decode(self, images, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0):
+        """Forward + decode chain as ONE stream operation (one CUDA graph in bf16 mode): ``images`` as in
+        :meth:`forward`; returns the engine-owned maps, the decode results stay in the engine's device tables
+        (:meth:`fetch`)."""
+        torch = _torch()
+        if images.device.type != "cuda" or not images.is_contiguous():
+            raise ValueError("images must be a contiguous CUDA tensor")
+        B, H, W, Cc = images.shape
+        if (H, W, Cc) != (self.height, self.width, 3) or B > self.max_batch:
+            raise ValueError(f"engine built for [<= {self.max_batch},{self.height},{self.width},3], got {tuple(images.shape)}")
+        if images.dtype not in (torch.uint8, torch.float32):
+            raise ValueError("images must be float32 or uint8")
+        heat, paf, _, _ = self._outputs(B, images.device)
+        _, s = self._device_tables()
+        _lib.check(self.lib.lwop_forward_decode(self.handle, images.data_ptr(), int(images.dtype == torch.uint8), B,
+                                                _MODES[mode], float(np.float32(thre1)), float(thre2), heat.data_ptr(),
+                                                paf.data_ptr(), C.byref(s), self._stream()), self.handle)
+        return heat, paf
+
     # -- decode stages, separately callable ------------------------------------------
     def nms_device(self, heat, factor: float, thre1: float, mode: int = 0):
         """Peak search + refinement on ``heat [B,h,w,14]`` (CUDA float32).  Returns the device peak table
@@ -283,14 +328,16 @@ class Engine:
                    self.handle)
         return peaks, pc, counts
 
-    def connect_device(self, paf, upsampled: bool, map_hw, img_hw, thre2: float, peaks, pc, counts):
+    def connect_device(self, paf, upsampled: bool, map_hw, img_hw, thre2: float, peaks, pc, counts,
+                       num_intermed_pts: int = 10, max_dist_thresh: float = 1.0):
         """find_connected_joints on the device peak table; returns ``limbs [B,13,MAX_PEAKS,5]`` (float64)."""
         torch = _torch()
         B = paf.shape[0]
         limbs = torch.zeros((B, _lib.NUM_LIMBS, _lib.MAX_PEAKS, 5), dtype=torch.float64, device=paf.device)
         _lib.check(self.lib.lwop_find_connected_joints(self.handle, paf.data_ptr(), int(bool(upsampled)), B,
                                                        int(map_hw[0]), int(map_hw[1]), int(img_hw[0]), int(img_hw[1]),
-                                                       float(thre2), peaks.data_ptr(), pc.data_ptr(), limbs.data_ptr(),
+                                                       float(thre2), int(num_intermed_pts), float(max_dist_thresh),
+                                                       peaks.data_ptr(), pc.data_ptr(), limbs.data_ptr(),
                                                        counts.data_ptr(), self._stream()), self.handle)
         return limbs
 
@@ -337,8 +384,7 @@ class Engine:
         One C call: H2D, forward, decode, D2H.  Returns a :class:`BatchResult`
         (and the host maps when ``want_maps``)."""
         torch = _torch()
-        if isinstance(images_host, np.ndarray):
-            images_host = torch.from_numpy(np.ascontiguousarray(images_host))
+        images_host = validate_host_images(images_host, self.height, self.width, self.max_batch)
         B = images_host.shape[0]
         is_u8 = images_host.dtype == torch.uint8
         hst = self._host_tables(B)
@@ -371,8 +417,7 @@ class Engine:
         (begin k+1 before end k) overlaps the upload of one with the kernels of the other.  ``images_host``
         must be pinned and stay alive until the matching ``infer_host_end``."""
         torch = _torch()
-        if isinstance(images_host, np.ndarray):
-            images_host = torch.from_numpy(np.ascontiguousarray(images_host))
+        images_host = validate_host_images(images_host, self.height, self.width, self.max_batch)
         B = images_host.shape[0]
         is_u8 = images_host.dtype == torch.uint8
         free = [t for t in self._async_tables if t["batch"] >= B and not t.get("busy")]

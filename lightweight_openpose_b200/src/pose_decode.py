@@ -211,9 +211,8 @@ def find_connected_joints(param, paf_upsamp, joint_list_per_joint_type, num_inte
     """Per limb type an ``(n, 5)`` float64 array ``(src_id, dst_id, score, i, j)`` -- or ``[]`` when either joint
     list is empty -- exactly as the reference returns (:188-301).  ``paf_upsamp`` is the PAF map already
     up-sampled to the frame ``[H, W, 26]`` (what ``decode_pose`` hands over, :487,493)."""
-    if num_intermed_pts != 10 or max_dist_thresh != 1:
-        raise NotImplementedError("the CUDA limb kernel implements the reference defaults "
-                                  "(num_intermed_pts=10, max_dist_thresh=1)")
+    if not 1 <= int(num_intermed_pts) <= 64:
+        raise ValueError("num_intermed_pts must be in 1..64")
     torch = _torch()
     engine.require_gpu(0)
     dev = torch.device("cuda", 0)
@@ -227,7 +226,8 @@ def find_connected_joints(param, paf_upsamp, joint_list_per_joint_type, num_inte
     peaks, pc = _peak_table_from_lists(joint_list_per_joint_type, dev)
     counts = torch.zeros((1, _lib.COUNTS), dtype=torch.int32, device=dev)
     e = _decode_engine(max(16, H), max(16, W), 1)
-    limbs = e.connect_device(paf[None], True, (H, W), (H, W), float(param['thre2']), peaks, pc, counts)
+    limbs = e.connect_device(paf[None], True, (H, W), (H, W), float(param['thre2']), peaks, pc, counts,
+                             int(num_intermed_pts), float(max_dist_thresh))
     lim, cnt = limbs[0].cpu().numpy(), counts[0].cpu().numpy()
     out = []
     for t, (a, b) in enumerate(joint_to_limb_heatmap_relationship):

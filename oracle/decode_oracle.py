@@ -253,10 +253,14 @@ def refine_peaks(heatmaps: np.ndarray, thre1: float, factor: float, use_cv2: boo
 # ----------------------------------------------------------------------------
 # D4: limb scoring -- pose_decode.py:188-301 (find_connected_joints)
 # ----------------------------------------------------------------------------
-def score_limbs(paf_up: np.ndarray, per_type: List[np.ndarray], thre2: float) -> List[np.ndarray]:
+def score_limbs(paf_up: np.ndarray, per_type: List[np.ndarray], thre2: float, num_intermed_pts: int = NUM_SAMPLES,
+                max_dist_thresh: float = 1) -> List[np.ndarray]:
     """Per limb type an array [m, 5] float64 ``(src_id, dst_id, score, i, j)``
-    -- for every source joint its single best destination (ties: first j)."""
+    -- for every source joint its single best destination (ties: first j).  ``num_intermed_pts`` and
+    ``max_dist_thresh`` are the reference's keyword arguments (:188): samples per candidate limb and the
+    multiple of the frame size beyond which a pair is skipped (:209,250)."""
     H, W = paf_up.shape[:2]
+    long_dist_thresh = np.array([W, H]) * max_dist_thresh          # (:209)
     out: List[np.ndarray] = []
     for t in range(NUM_LIMBS):
         src = per_type[LIMB_JOINTS[t][0]]
@@ -270,17 +274,17 @@ def score_limbs(paf_up: np.ndarray, per_type: List[np.ndarray], thre2: float) ->
             best, best_row = 0.0, None                             # (:243)
             for j, b in enumerate(dst):
                 d = b[:2] - a[:2]                                  # (:249)
-                if abs(d[0]) > W or abs(d[1]) > H:                 # (:209,250)
+                if (np.abs(d) > long_dist_thresh).any():           # (:250)
                     continue
                 norm = np.sqrt(np.sum(d ** 2)) + 1e-8              # (:255)
                 u = d / norm
-                xs = np.round(np.linspace(a[0], b[0], num=NUM_SAMPLES)).astype(np.intp)   # (:260-264)
-                ys = np.round(np.linspace(a[1], b[1], num=NUM_SAMPLES)).astype(np.intp)
+                xs = np.round(np.linspace(a[0], b[0], num=num_intermed_pts)).astype(np.intp)   # (:260-264)
+                ys = np.round(np.linspace(a[1], b[1], num=num_intermed_pts)).astype(np.intp)
                 vx = paf_up[ys, xs, cx].astype(np.float64)         # f32 samples promoted (:267-270)
                 vy = paf_up[ys, xs, cy].astype(np.float64)
                 s = vx * u[0] + vy * u[1]
                 mean = s.mean()                                    # (:271)
-                if (np.count_nonzero(s > thre2) > 0.8 * NUM_SAMPLES   # (:276-277)
+                if (np.count_nonzero(s > thre2) > 0.8 * num_intermed_pts   # (:276-277)
                         and mean > thre2 and mean > best):         # (:283,285)
                     best = mean
                     best_row = (a[3], b[3], mean, i, j)            # (:287)

@@ -55,3 +55,19 @@ def decode_golden():
 def decode_golden_noipp():
     """Reference module with cv2.ipp.setUseIPP(False): OpenCV's own float32 arithmetic (bit-exact target)."""
     return _load_golden("decode_golden_noipp.npz")
+
+
+@pytest.fixture(scope="session")
+def decode_extra_golden():
+    """Reference module (IPP off) on the dense 46x82 frame and with non-default find_connected_joints keyword
+    arguments (tests/golden/make_decode_extra_golden.py)."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "decode_extra_golden.npz"))
+    dense = {"heat": z["dense_46x82/heat"], "paf": z["dense_46x82/paf"], "hw": tuple(int(v) for v in z["dense_46x82/hw"]),
+             "joint_list": z["dense_46x82/joint_list"], "limbs": [z[f"dense_46x82/limb{t}"] for t in range(13)],
+             "persons": z["dense_46x82/persons"], "joints": z["dense_46x82/joints"]}
+    settings = [(int(n), float(thr)) for n, thr in z["params/settings"]]
+    params = {"heat": z["params/heat"], "paf": z["params/paf"], "joint_list": z["params/joint_list"],
+              "settings": settings,
+              "limbs": [[z[f"params/{k}/limb{t}"] for t in range(13)] for k in range(len(settings))]}
+    return dense, params, {"thre1": float(z["thre"][0]), "thre2": float(z["thre"][1])}

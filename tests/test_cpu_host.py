@@ -102,7 +102,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 17
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.lwop_abi_version() == 1
+    assert lib.lwop_abi_version() == 2
     assert lib.lwop_same_out(368, 2) == 184 and lib.lwop_same_out(45, 2) == 23
     assert lib.lwop_error_string(-4) == b"decode table overflow"
 
@@ -164,3 +164,23 @@ def test_u8_normalisation_is_single_rounding():
     ref = (u / 255.).astype(np.float32)
     assert np.array_equal(ref, (u.astype(np.float64) / 255.0).astype(np.float32))
     assert np.array_equal(synth.synth_batch([0], 32, 32)[0], (synth.synth_image(0, 32, 32) / 255.).astype(np.float32))
+
+
+def test_host_frame_validation():
+    """Engine.infer_host / infer_host_begin hand a raw pointer to C: shape, batch, dtype and contiguity are checked
+    (and float64 frames -- the reference's own `img / 255.` -- cast to float32) before that."""
+    import torch
+    from lightweight_openpose_b200.engine import validate_host_images as val
+    u8 = np.zeros((2, 64, 48, 3), np.uint8)
+    out = val(u8, 64, 48, 4)
+    assert out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (2, 64, 48, 3)
+    f64 = np.random.default_rng(0).random((1, 64, 48, 3))
+    out = val(f64, 64, 48, 4)
+    assert out.dtype == torch.float32 and np.array_equal(out.numpy(), f64.astype(np.float32))
+    assert val(torch.zeros((1, 64, 48, 3), dtype=torch.float16), 64, 48, 4).dtype == torch.float32
+    nc = torch.zeros((2, 64, 48, 6), dtype=torch.float32)[..., ::2]
+    assert not nc.is_contiguous() and val(nc, 64, 48, 4).is_contiguous()
+    for bad in (np.zeros((2, 48, 64, 3), np.uint8), np.zeros((64, 48, 3), np.uint8), np.zeros((5, 64, 48, 3), np.uint8),
+                np.zeros((0, 64, 48, 3), np.uint8), np.zeros((2, 64, 48, 3), np.int32), np.zeros((2, 64, 48, 4), np.uint8)):
+        with pytest.raises(ValueError):
+            val(bad, 64, 48, 4)

@@ -206,20 +206,118 @@ def test_grouping_on_adversarial_tables(spec):
 
 
 def test_capacity_limits_fail_loudly():
-    """The device tables have fixed capacities the reference does not have (128 peaks per joint channel, 128 persons):
+    """The device tables have fixed capacities the reference does not have (256 peaks per joint channel, 256 persons):
     exceeding one is an error, never a silently truncated result."""
     from lightweight_openpose_b200 import _lib
-    heat = np.zeros((96, 96, 14), np.float32)
-    heat[3::6, 3::6, 0] = 0.9                       # 16 x 16 = 256 isolated peaks, 6 px apart (> the radius-5 suppression)
-    assert len(orc.greedy_radius_peaks(heat[:, :, 0], 0.1)) == 256
+    heat = np.zeros((108, 108, 14), np.float32)
+    heat[3::6, 3::6, 0] = 0.9                       # 18 x 18 = 324 isolated peaks, 6 px apart (> the radius-5 suppression)
+    assert len(orc.greedy_radius_peaks(heat[:, :, 0], 0.1)) == 324
     with pytest.raises(_lib.LwopError):
         pose_decode.NMS(PARAM, heat, 8.0)
     with pytest.raises(_lib.LwopError):
-        pose_decode.decode_pose(np.zeros((768, 768, 3), np.uint8), PARAM, heat, np.zeros((96, 96, 26), np.float32))
-    heat[:, :, 0] = 0.0
-    heat[3::12, 3::6, 0] = 0.9                      # 8 x 16 = 128 peaks: exactly the capacity, no error
+        pose_decode.decode_pose(np.zeros((864, 864, 3), np.uint8), PARAM, heat, np.zeros((108, 108, 26), np.float32))
+    heat = np.zeros((96, 96, 14), np.float32)
+    heat[3::6, 3::6, 0] = 0.9                       # 16 x 16 = 256 peaks: exactly the capacity, no error
     got = pose_decode.NMS(PARAM, heat, 8.0)
-    assert len(got[0]) == 128 and all(len(g) == 0 for g in got[1:])
+    assert len(got[0]) == 256 and all(len(g) == 0 for g in got[1:])
     eng = engine.Engine(64, 64, max_batch=2, device=0)
     with pytest.raises(ValueError):
         eng.forward(torch.zeros((3, 64, 64, 3), device="cuda"))
+
+
+def test_decode_dense_46x82_frame_matches_reference_golden(decode_extra_golden):
+    """BASELINE configs[3] frame size with every heat-map pixel above thre1: ~104 peaks per channel (more than the 128-row
+    tables of round 1 could take in a denser packing), 1288 connections, 141 persons -- the reference returns a result
+    and the CUDA chain returns the same one, bit for bit (register-resident grouping hands over to the general kernel)."""
+    dense, _, param = decode_extra_golden
+    res = pose_decode.decode_pose_batch(dense["hw"], param, dense["heat"][None], dense["paf"][None])[0]
+    compare_decode(_as_dict(res), dense, float_tol=0.0, f64_tol=1e-13)
+    # batched next to light frames: the fast / general grouping split is per image
+    h3, p3, _ = synth.synth_scene(3, 3, 368, 656)
+    heat = np.stack([h3, dense["heat"], h3])
+    paf = np.stack([p3, dense["paf"], p3])
+    out = pose_decode.decode_pose_batch(dense["hw"], param, heat, paf)
+    compare_decode(_as_dict(out[1]), dense, float_tol=0.0, f64_tol=1e-13)
+    ref3 = orc.decode_detail((368, 656), param, h3, p3, use_cv2=False)
+    for k in (0, 2):
+        compare_decode(_as_dict(out[k]), ref3, float_tol=0.0, f64_tol=1e-13)
+
+
+def test_find_connected_joints_keyword_arguments(decode_extra_golden):
+    """num_intermed_pts / max_dist_thresh of the reference signature (:188), against the reference's own output."""
+    _, params, param = decode_extra_golden
+    jl = params["joint_list"]
+    per_type = [jl[jl[:, 5] == j][:, :5] for j in range(14)]
+    paf_up = orc._resize_full(params["paf"], 368, 368, False)
+    for (n, thr), want in zip(params["settings"], params["limbs"]):
+        got = pose_decode.find_connected_joints(param, paf_up, per_type, num_intermed_pts=n, max_dist_thresh=thr)
+        for t in range(13):
+            a, b = np.asarray(got[t], dtype=np.float64).reshape(-1, 5), want[t].reshape(-1, 5)
+            assert a.shape == b.shape, (n, thr, t)
+            if a.size:
+                assert np.array_equal(a[:, [0, 1, 3, 4]], b[:, [0, 1, 3, 4]]), (n, thr, t)
+                assert np.abs(a[:, 2] - b[:, 2]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        pose_decode.find_connected_joints(param, paf_up, per_type, num_intermed_pts=65)
+
+
+def test_peak_search_on_tied_plateaus():
+    """Exact ties: the reference orders candidates with an unstable argsort, so which pixel of a flat plateau survives
+    is implementation-defined there.  Asserted here: what does NOT depend on the tie order -- kept peaks
+    are pairwise farther than 5 px apart, every candidate is within 5 px of a kept peak of equal or higher value,
+    strict maxima are always kept -- and that the CUDA kernel and the oracle apply the same documented rule (larger
+    row-major index first)."""
+    rng = np.random.default_rng(77)
+    heat = np.zeros((46, 46, 14), np.float32)
+    heat[:, :, 0] = 0.5                                            # one plateau over the whole map
+    heat[10:20, 10:30, 1] = 0.7                                    # plateau + strict maxima
+    heat[5, 5, 1], heat[40, 40, 1] = 0.9, 0.95
+    heat[:, :, 2] = np.round(rng.random((46, 46)) * 4) / 4         # quantised map: many ties
+    for ch in range(3):
+        got = pose_decode.find_peaks_v2(PARAM, heat[:, :, ch]).reshape(-1, 2)
+        want = orc.greedy_radius_peaks(heat[:, :, ch], 0.1)
+        assert np.array_equal(got, want)
+        xy = got.astype(np.int64)
+        d2 = ((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1)
+        assert (d2[~np.eye(len(xy), dtype=bool)] > 25).all()
+        vals = heat[xy[:, 1], xy[:, 0], ch]
+        assert (np.diff(vals) <= 0).all()                          # best first
+        ys, xs = np.nonzero(heat[:, :, ch] > 0.1)
+        for y, x in zip(ys, xs):
+            near = ((xy[:, 0] - x) ** 2 + (xy[:, 1] - y) ** 2) <= 25
+            assert near.any() and vals[near].max() >= heat[y, x, ch]
+    got1 = pose_decode.find_peaks_v2(PARAM, heat[:, :, 1]).reshape(-1, 2).tolist()
+    assert [40, 40] in got1 and [5, 5] in got1
+
+
+def test_forward_decode_single_graph_equals_separate_calls():
+    """lwop_forward_decode (forward + decode chain replayed from one CUDA graph) == lwop_forward then lwop_decode."""
+    from lightweight_openpose_b200 import checkpoint
+    eng = engine.Engine(368, 368, max_batch=4, device=0)
+    variables, src = checkpoint.load_or_synthesize()
+    eng.load_variables(variables, src)
+    x = torch.from_numpy(np.stack([synth.synth_image(s, 368, 368) for s in range(4)])).cuda()
+    heat, paf = eng.forward(x)
+    want = eng.decode(heat.clone(), paf.clone(), (368, 368))
+    for _ in range(3):                                             # eager pass, capture, replay
+        eng.forward_decode(x)
+        got = eng.fetch(4)
+        assert np.array_equal(got.counts, want.counts)
+        assert np.array_equal(got.joints, want.joints) and np.array_equal(got.persons, want.persons)
+        assert np.array_equal(got.limbs, want.limbs) and np.array_equal(got.keypoints, want.keypoints)
+    assert int(want.counts[:, 0].sum()) > 0
+
+
+def test_decode_parity_1000_frames():
+    """BASELINE configs[4] in the driver-run suite: the standalone decode on 1000 generator scenes (1-20 persons, seed =
+    frame index) against the oracle -- integer fields and float32 scores exact, float64 scores <= 1e-12.  The 10 000
+    frame run of the same loop is tools/decode_parity_10k.py (profiles/)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import decode_parity_10k
+    line = decode_parity_10k.run(1000, time_limit=600.0)
+    assert line["frames_checked"] == 1000
+    assert line["frames_with_any_mismatch"] == 0, line
+    assert line["max_abs_joint_score_diff"] == 0.0
+    assert line["persons"] > 5000

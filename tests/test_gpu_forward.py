@@ -60,6 +60,43 @@ def test_forward_batch64_matches_oracle_and_is_batch_invariant(variables):
     assert np.array_equal(h2.cpu().numpy(), h[37:41]) and np.array_equal(p2.cpu().numpy(), p[37:41])
 
 
+def test_forward_batch64_fp32_check_and_bf16_on_every_image(variables):
+    """BASELINE configs[1] as written: batch 64 at 368x368, forward only, fp32 check mode (<= 1e-4) and bf16 (<= 2e-2)
+    against the oracle on ALL 64 images."""
+    x = synth.synth_batch(range(64), 368, 368)
+    oh, op = ForwardOracle(variables)(x)
+    xd = torch.from_numpy(x).cuda()
+    h32, p32 = (t.cpu().numpy() for t in lightweight_openpose(xd, 14, 26, is_training=False, mode="fp32"))
+    e32 = np.maximum(np.abs(h32 - oh).reshape(64, -1).max(1), np.abs(p32 - op).reshape(64, -1).max(1))
+    assert e32.max() <= TOL_FP32, e32
+    h16, p16 = (t.cpu().numpy() for t in lightweight_openpose(xd, 14, 26, is_training=False))
+    e16 = np.maximum(np.abs(h16 - oh).reshape(64, -1).max(1), np.abs(p16 - op).reshape(64, -1).max(1))
+    print("batch 64: fp32-check max-abs", e32.max(), "bf16 max-abs", e16.max())
+    assert e16.max() <= TOL_BF16, e16
+
+
+def test_two_handles_with_different_weights_on_one_device(variables):
+    """Every layer's weights belong to the handle (the first conv's taps travel as a kernel parameter): two engines
+    with different checkpoints on one device must not see each other's layer 0."""
+    other = {k: (v * np.float32(2.0) if k == "BackBone/conv2d/kernel" else v) for k, v in variables.items()}
+    assert any(not np.array_equal(other[k], variables[k]) for k in variables)
+    x = synth.synth_batch([1, 2], 256, 256)
+    xd = torch.from_numpy(x).cuda()
+    ea, eb = engine.Engine(256, 256, max_batch=2), engine.Engine(256, 256, max_batch=2)
+    ea.load_variables(variables, "a")
+    eb.load_variables(other, "b")                     # loaded last: a process-global table would now hold b's taps
+    for mode, tol in (("bf16", TOL_BF16), ("fp32", TOL_FP32)):
+        ha, pa = (t.clone() for t in ea.forward(xd, mode=mode))
+        hb, pb = (t.clone() for t in eb.forward(xd, mode=mode))
+        ha2, _ = ea.forward(xd, mode=mode)            # again after b ran
+        assert torch.equal(ha, ha2)
+        oa, _ = ForwardOracle(variables)(x)
+        ob, _ = ForwardOracle(other)(x)
+        gap = _maxabs(oa, ob)                         # the two checkpoints differ by ~1 at the output
+        assert gap > 0.5
+        assert _maxabs(ha.cpu().numpy(), oa) <= tol and _maxabs(hb.cpu().numpy(), ob) <= max(tol, 0.05 * gap)
+
+
 def test_eager_net_factory_path_matches_executor(variables):
     x = synth.synth_batch([3], 256, 256)
     h, p = lightweight_openpose(x, 14, 26, is_training=False, mode="fp32")

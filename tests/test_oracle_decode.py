@@ -208,3 +208,36 @@ def test_grouping_restatement_on_adversarial_tables_matches_live_reference():
         assert got.shape == want.shape, (seed, got.shape, want.shape)
         if want.size:
             assert np.array_equal(got, want), seed
+
+
+def _per_type_from_joint_list(jl):
+    jl = np.asarray(jl, dtype=np.float64).reshape(-1, 6)
+    return [jl[jl[:, 5] == j][:, :5] for j in range(14)]
+
+
+def test_oracle_dense_frame_matches_reference_golden(decode_extra_golden):
+    """46x82 maps with every pixel above thre1 (BASELINE configs[3] frame size): ~104 peaks per channel, 1288
+    connections, 141 persons in the reference's own output -- all reproduced exactly."""
+    dense, _, param = decode_extra_golden
+    got = orc.decode_detail(dense["hw"], param, dense["heat"], dense["paf"], use_cv2=False)
+    compare_decode(got, dense, float_tol=0.0, f64_tol=1e-13)
+    assert max(np.bincount(dense["joint_list"][:, 5].astype(int))) > 100
+
+
+def test_oracle_limb_keyword_arguments_match_reference_golden(decode_extra_golden):
+    """find_connected_joints(num_intermed_pts, max_dist_thresh) (reference :188) for nine settings."""
+    _, params, param = decode_extra_golden
+    per_type = _per_type_from_joint_list(params["joint_list"])
+    paf_up = orc._resize_full(params["paf"], 368, 368, False)
+    differs = 0
+    for (n, thr), want in zip(params["settings"], params["limbs"]):
+        got = orc.score_limbs(paf_up, per_type, param["thre2"], num_intermed_pts=n, max_dist_thresh=thr)
+        for t in range(13):
+            a, b = got[t].reshape(-1, 5), want[t].reshape(-1, 5)
+            assert a.shape == b.shape, (n, thr, t)
+            if a.size:
+                assert np.array_equal(a[:, [0, 1, 3, 4]], b[:, [0, 1, 3, 4]]), (n, thr, t)
+                assert np.abs(a[:, 2] - b[:, 2]).max() <= 1e-13
+        base = params["limbs"][params["settings"].index((9, 1.0))]
+        differs += any(not np.array_equal(want[t], base[t]) for t in range(13))
+    assert differs >= 5          # the settings do change the result

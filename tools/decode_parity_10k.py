@@ -9,7 +9,6 @@ import json
 import os
 import sys
 import time
-from multiprocessing import Pool
 
 import numpy as np
 
@@ -37,14 +36,12 @@ def oracle_one(i):
     return i, h, p, d
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=10000)
-    ap.add_argument("--procs", type=int, default=os.cpu_count() or 1)
-    ap.add_argument("--chunk", type=int, default=256)
-    ap.add_argument("--time-limit", type=float, default=1500.0)
-    ap.add_argument("--out", default=None)
-    args = ap.parse_args()
+def run(frames, procs=None, chunk=256, time_limit=1500.0):
+    """The parity loop; returns the summary dict.  Oracle workers are spawned (not forked): the calling process may
+    already hold a CUDA context (pytest)."""
+    import multiprocessing as mp
+    from types import SimpleNamespace
+    args = SimpleNamespace(frames=frames, procs=procs or (os.cpu_count() or 1), chunk=chunk, time_limit=time_limit)
     FLOAT_TOL = 1e-5 if USE_IPP else 0.0
     from lightweight_openpose_b200.src import pose_decode
     from test_oracle_decode import compare_decode
@@ -53,7 +50,7 @@ def main():
     max_float = 0.0
     persons = joints = 0
     bad_frames = []
-    with Pool(args.procs) as pool:
+    with mp.get_context("spawn").Pool(args.procs) as pool:
         for c0 in range(0, args.frames, args.chunk):
             if time.time() - t0 > args.time_limit:
                 break
@@ -85,6 +82,18 @@ def main():
                           "; float64 limb/person scores <= 1e-12"),
             "oracle_procs": args.procs,
             "seconds": round(time.time() - t0, 1)}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=10000)
+    ap.add_argument("--procs", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--time-limit", type=float, default=1500.0)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    line = run(args.frames, args.procs, args.chunk, args.time_limit)
     print(json.dumps(line))
     if args.out:
         with open(args.out, "w") as fh:
