@@ -3,11 +3,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-One process per GPU (under torchrun for N > 1; ranks are independent replicas,
-the only cross-rank traffic is the barrier and the max-reduction of the time).
-A step is one pass of the whole path -- network forward (bf16 tensor-core
-kernels) + on-device pose decode -- over one batch of synthetic frames.
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+A step is one pass of the whole path -- network forward (bf16 tensor-core kernels) + on-device pose decode -- over
+ONE batch of 256 synthetic frames (BASELINE.json configs[2]).  With N GPUs (one process per GPU under torchrun) the
+batch is sharded 256/N frames per rank (strong scaling); there is no data-path collective, the per-image result
+tables are gathered on rank 0 through host shared memory.  NCCL carries only the barrier and the max-reduction of
+the elapsed time.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
 from __future__ import annotations
 
@@ -134,10 +134,10 @@ def cpu_path_images_per_s(n_images: int, threads: int):
     return n_images / dt, dt
 
 
-def workload_name(batch: int, world: int) -> str:
+def workload_name(global_batch: int) -> str:
     """config.workload, shared by both arms so the driver compares like with like."""
-    return (f"batch {batch} per GPU, 368x368 forward+decode (BASELINE.json configs[2]), "
-            f"{world} independent replica(s), no collective on the data path")
+    return (f"one batch of {global_batch} frames per step, 368x368 forward+decode, batch-sharded over the GPUs of the "
+            "run with a host-side result gather on rank 0 (BASELINE.json configs[2]); no collective on the data path")
 
 
 def run_reference(args, rank: int, world: int):
@@ -157,13 +157,18 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch, world), "global_batch": args.batch * world, "height": H,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "global_batch": args.batch, "height": H,
                    "width": W, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
                    "reference_arm": f"bounded sample of that workload: each step is the reference's batch-1 serial "
                                     f"loop (model_test.py:82-99) over {sample} of its frames; CPU port of the reference "
                                     "path (torch-CPU fp32 forward on all host threads + numpy/cv2 decode, one thread "
-                                    "as in the reference loop), stand-in for TF-CPU: TensorFlow is not installable here"},
+                                    "as in the reference loop), stand-in for TF-CPU: TensorFlow is not installable here",
+                   "why_steps_and_config_differ": "a CPU step of the full 256-frame batch takes ~11 s, so the arm times a "
+                                                  f"bounded {sample}-frame sample per step and clamps warm-up to 2 (each "
+                                                  "warm-up is a full CPU pass); the metric is a throughput (images/s), "
+                                                  "which does not depend on the sample size; it runs on the host cores "
+                                                  "only, so its value is the same at every --gpus N"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} frames x {args.steps} steps"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,24 +210,206 @@ def step_work(desc, batch):
     return flops, float(in_b + out_b) * batch
 
 
+def roofline_record(eng, x_dev, batch, mode, dump_steps=None):
+    """Live per-kernel timing (graph-less forward, CUDA events around every launch) -> (roofline, per-class table,
+    forward ms).  `achieved` = algorithmic flops (or bytes) of the dominant kernel class / its measured time."""
+    descs = eng.step_descs()
+    acc = np.zeros(len(descs))
+    n_prof = 5
+    eng.profile_forward(x_dev, mode=mode)
+    for _ in range(n_prof):
+        acc += np.asarray(eng.profile_forward(x_dev, mode=mode))
+    acc /= n_prof
+    classes = {}
+    rows = []
+    for i, (d, ms) in enumerate(zip(descs, acc)):
+        cls = classify_step(d, descs[i + 1] if i + 1 < len(descs) else None)
+        if cls is None:
+            continue
+        c = classes.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        fl, by = step_work(d, batch)
+        if d[9] == 2:        # fused: depthwise + pointwise flops; bytes = layer input + layer output only
+            fl2, _ = step_work(descs[i + 1], batch)
+            oh, ow = -(-d[2] // d[7]), -(-d[3] // d[7])
+            fl += fl2
+            by = 2.0 * (d[2] * d[3] * d[4] + oh * ow * descs[i + 1][5]) * batch
+        if d[9] == 4:        # fused head pair: flops of the four 1x1 convs; bytes = shared input + two narrow outputs
+            fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
+            by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
+        if d[9] == 5:        # fused stem: first conv + depthwise + pointwise; bytes = frame in + 64-channel map out
+            fl = sum(step_work(descs[i + k], batch)[0] for k in range(3))
+            oh, ow = -(-d[2] // 2), -(-d[3] // 2)
+            by = (float(x_dev.element_size()) * d[2] * d[3] * 3 + 2.0 * oh * ow * descs[i + 2][5]) * batch
+        c["ms"] += ms
+        c["flops"] += fl
+        c["bytes"] += by
+        c["launches"] += 1
+        rows.append({"layer": d[0], "kind": cls, "in_hw": [d[2], d[3]], "cin": d[4],
+                     "cout": descs[i + 1][5] if d[9] == 2 else d[5], "k": d[6], "stride": d[7], "dil": d[8],
+                     "ms": round(float(ms), 4), "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
+                     "gbs": round(by / (ms * 1e-3) / 1e9, 1)})
+    if dump_steps:
+        with open(dump_steps, "w") as fh:
+            for r in rows:
+                fh.write(json.dumps(r) + "\n")
+    peaks = measured_peaks()
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    dc = classes[dom]
+    # a fused separable layer is bounded by whichever of the two rooflines is slower for its shape mix:
+    # report it against the tensor roofline when its tensor time exceeds its HBM time
+    tensor_bound = dom.startswith("gemm") or dom.startswith("head") or (
+        dom.startswith("sep") and dc["flops"] / (peaks["bf16_tflops_sustained"] * 1e12) > dc["bytes"] / (peaks["hbm_gbs"] * 1e9))
+    if tensor_bound:
+        achieved = dc["flops"] / (dc["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "frac_burst": achieved / peaks["bf16_tflops"],
+                "peak_burst": peaks["bf16_tflops"], "traffic": None}
+    else:
+        achieved = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "frac_burst": achieved / peaks["hbm_gbs"], "traffic": None}
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr.get("batch") == batch and dom in tr["traffic_bytes_per_launch"]:
+            roof["traffic"] = tr["traffic_bytes_per_launch"][dom]
+            roof["traffic_source"] = tr.get("source", "profiles/ncu_traffic.json (ncu --set full, one launch)")
+            roof["algorithmic_bytes_per_launch"] = dc["bytes"] / dc["launches"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roof["kernel"] = dom
+    roof["launches_per_step"] = dc["launches"]
+    roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
+    roof["peak_source"] = peaks["source"] + (" (sustained; frac_burst is against the burst figure)" if tensor_bound else "")
+    per_class = {}
+    for k, c in classes.items():
+        per_class[k] = {"ms": round(c["ms"], 4), "launches": c["launches"],
+                        "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 2),
+                        "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)}
+    return roof, per_class, float(acc.sum()), peaks
+
+
+def latency_record(variables, source, device, mode):
+    """Batch-1 latency, the reference loop's shape (model_test.py:39 placeholder [1,None,None,3], :68 one sess.run
+    per frame + decode_pose): one synchronous lwop_infer_host call per uint8 host frame (upload, forward, decode,
+    download), and the device-resident forward+decode graph alone."""
+    import torch
+    from lightweight_openpose_b200 import engine, synth
+    eng = engine.Engine(H, W, max_batch=1, device=device)
+    eng.load_variables(variables, source)
+    frames = [torch.from_numpy(synth.synth_image(s, H, W)[None]).pin_memory() for s in range(8)]
+    x_dev = [f.cuda() for f in frames]
+    for i in range(10):
+        eng.infer_host(frames[i % 8], mode=mode)
+        eng.forward_decode(x_dev[i % 8], mode=mode)
+    torch.cuda.synchronize()
+    lat = []
+    for i in range(200):
+        t0 = time.perf_counter()
+        eng.infer_host(frames[i % 8], mode=mode)
+        lat.append(1e3 * (time.perf_counter() - t0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(200):
+        eng.forward_decode(x_dev[i % 8], mode=mode)
+    e1.record()
+    torch.cuda.synchronize()
+    eng.close()
+    lat.sort()
+    return {"host_frame_to_result_ms_median": round(lat[len(lat) // 2], 4), "host_frame_to_result_ms_p99": round(lat[197], 4),
+            "device_forward_decode_ms": round(e0.elapsed_time(e1) / 200, 4), "frames": 200,
+            "what": "batch 1, 368x368, one synchronous lwop_infer_host per uint8 host frame (wall clock, upload + "
+                    "forward + decode + download), and back-to-back device-resident forward+decode graph launches"}
+
+
+def dense_scene_record(variables, source, device, mode, cpu_frames: int):
+    """BASELINE.json configs[3]: 656x368 frames, 20-person scenes stressing the peak search and the grouping.
+    decode-only: the scenes' heat maps / PAFs (label generator) fed to the decode chain; forward+decode:
+    the forward on synthetic 656x368 frames followed by the decode of those scene maps (the synthetic weights cannot
+    produce 20-person maps, so the two halves are chained on separate buffers).  The CPU port on the same scenes
+    stands beside it."""
+    import torch
+    from lightweight_openpose_b200 import engine, synth
+    HH, WW, B = 368, 656, 64
+    eng = engine.Engine(HH, WW, max_batch=B, device=device)
+    eng.load_variables(variables, source)
+    hs, ps = zip(*[synth.synth_scene(1000 + s, 20, HH, WW)[:2] for s in range(16)])
+    heat = torch.from_numpy(np.concatenate([np.stack(hs)] * 4)[:B]).cuda()
+    paf = torch.from_numpy(np.concatenate([np.stack(ps)] * 4)[:B]).cuda()
+    base = np.stack([synth.synth_image(s, HH, WW) for s in range(16)])
+    x = torch.from_numpy(np.concatenate([base] * 4)[:B]).cuda()
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    dec_ms = timed(lambda: eng.decode_device(heat, paf, (HH, WW), PARAM["thre1"], PARAM["thre2"]))
+    res = eng.fetch(B)
+
+    def both():
+        eng.forward(x, mode=mode)
+        eng.decode_device(heat, paf, (HH, WW), PARAM["thre1"], PARAM["thre2"])
+    both_ms = timed(both)
+    rec = {"height": HH, "width": WW, "batch": B, "persons_per_image": float(res.counts[:, 1].mean()),
+           "joints_per_image": float(res.counts[:, 0].mean()),
+           "decode_only_images_per_s": B / (dec_ms * 1e-3), "decode_ms_per_batch": round(dec_ms, 4),
+           "forward_decode_images_per_s": B / (both_ms * 1e-3), "forward_decode_ms_per_batch": round(both_ms, 4)}
+    eng.close()
+    if cpu_frames > 0:
+        from oracle import decode_oracle
+        from oracle.forward_oracle import ForwardOracle
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        orc = ForwardOracle(variables)
+        img0 = np.zeros((HH, WW, 3), np.uint8)
+        t0 = time.perf_counter()
+        for s in range(cpu_frames):
+            decode_oracle.decode(img0, PARAM, hs[s % 16], ps[s % 16], draw=False)
+        t_dec = (time.perf_counter() - t0) / cpu_frames
+        orc((base[0] / 255.).astype(np.float32)[None])
+        t0 = time.perf_counter()
+        for s in range(cpu_frames):
+            orc((base[s % 16] / 255.).astype(np.float32)[None])
+        t_fwd = (time.perf_counter() - t0) / cpu_frames
+        rec["cpu_port"] = {"decode_only_images_per_s": 1.0 / t_dec, "forward_decode_images_per_s": 1.0 / (t_dec + t_fwd),
+                           "frames": cpu_frames, "cores": os.cpu_count() or 1, "kind": "port"}
+    return rec
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
-    from lightweight_openpose_b200 import checkpoint, engine
+    from lightweight_openpose_b200 import checkpoint, engine, replicas
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL logs its version there)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    batch = args.batch
-    eng = engine.Engine(H, W, max_batch=batch, device=local_rank, fuse_separable=not args.no_fuse)
+    G = args.batch                                   # ONE batch of G frames per step, sharded over the ranks
+    lo, hi = replicas.shard_bounds(G, world, rank)
+    b = hi - lo
+    lanes = max(1, args.lanes)
     variables, source = checkpoint.load_or_synthesize()
-    eng.load_variables(variables, source)
+    pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank)
+    pool.load_variables(variables, source)
+    eng0 = pool.engines[0]
 
-    frames_u8 = make_frames(batch)
+    frames_u8 = make_frames(G)[lo:hi]                # this rank's slice of the batch
+    # device-resident inputs: enough distinct float32 copies that a buffer is re-read only after > L2 of other inputs
+    # (on top of the ~19 MB of activations per frame written in between); buffer k always goes to lane k % lanes
+    in_bytes = b * H * W * 3 * 4
+    n_in = lanes * max(1, -(-int(160e6 // in_bytes + 1) // lanes))
     x_host = torch.from_numpy((frames_u8 / 255.).astype(np.float32)).pin_memory()      # reference feed: img / 255.
-    x_dev = x_host.cuda(non_blocking=True)
+    x_devs = [torch.roll(x_host, k, 0).cuda() for k in range(n_in)]
     torch.cuda.synchronize()
 
     def barrier():
@@ -231,186 +418,126 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        heat, paf = eng.forward(x_dev, mode=args.mode)
-        eng.decode_device(heat, paf, (H, W), PARAM["thre1"], PARAM["thre2"])
-        return heat, paf
+    seq = {"dev": 0}
 
-    # ---- device-resident throughput ("value") ----
-    for _ in range(args.warmup):
-        step_device()
+    def steps_device(n):
+        pool.fork()
+        for _ in range(n):
+            pool.step_device(x_devs[seq["dev"] % n_in], args.mode, PARAM["thre1"], PARAM["thre2"])
+            seq["dev"] += 1
+        pool.join()
+
+    # ---- device-resident throughput ("value"): K steps, up to `lanes` steps in flight on independent streams ----
+    steps_device(n_in)                               # builds every (lane, input buffer) CUDA graph
+    steps_device(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    eng.launch_count(reset=True)
+    for e in pool.engines:
+        e.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        step_device()
+    steps_device(args.steps)
     ev1.record()
     barrier()
-    launches = eng.launch_count()
+    launches = sum(e.launch_count() for e in pool.engines)
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    res = eng.fetch(batch)               # untimed: decode load of the workload, for the config record
+    res = eng0.fetch(b)                  # untimed: decode load of the workload, for the config record
     joints_per_img = float(res.counts[:, 0].mean())
     persons_per_img = float(res.counts[:, 1].mean())
 
-    if args.chunk > 0:
-        eng.set_option("chunk", args.chunk)
-    sweep = {}
-    if args.sweep_chunks and rank == 0:
-        for c in (32, 64, 128, 256):
-            if c > batch:
-                continue
-            eng.set_option("chunk", c)
-            sw = torch.from_numpy(frames_u8).pin_memory()
-            for _ in range(2):
-                eng.infer_host(sw, mode=args.mode)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(5):
-                eng.infer_host(sw, mode=args.mode)
-            torch.cuda.synchronize()
-            sweep[c] = round(1e3 * (time.perf_counter() - t0) / 5, 3)
-        eng.set_option("chunk", max(args.chunk, 0))
-    # ---- end to end through the host-buffer C entries (lwop_infer_host_begin / _end) ----
-    # Frames start in pinned HOST memory as uint8 (what cv2.imread / VideoCapture hand the reference loop,
-    # model_test.py:59-65); every step uploads its frames, runs `/ 255.` + forward + decode on the device and
-    # downloads the result tables.  Two batches are kept in flight (begin k+1, then end k), the way a serving loop
-    # drives the library, so the upload of one batch overlaps the kernels of the previous one; all K uploads and K
-    # downloads happen inside the timed region.
-    u8_a = torch.from_numpy(frames_u8).pin_memory()
-    u8_b = torch.from_numpy(np.ascontiguousarray(frames_u8[::-1])).pin_memory()
+    # the same with ONE step in flight (each step's kernels start after the previous step's have finished)
+    def one_at_a_time(n):
+        for i in range(n):
+            eng0.forward_decode(x_devs[(i * lanes) % n_in], args.mode, PARAM["thre1"], PARAM["thre2"])
+    cur = torch.cuda.current_stream()
+    eng0.stream.wait_stream(cur)
+    one_at_a_time(3)
+    barrier()
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record(eng0.stream)
+    one_at_a_time(args.steps)
+    es1.record(eng0.stream)
+    barrier()
+    ms_serial = es0.elapsed_time(es1)
 
-    def run_e2e(bufs, steps):
-        ticket = eng.infer_host_begin(bufs[0], mode=args.mode)
-        out = None
-        for i in range(1, steps):
-            nxt = eng.infer_host_begin(bufs[i % len(bufs)], mode=args.mode)
-            out = eng.infer_host_end(ticket)
-            ticket = nxt
-        out = eng.infer_host_end(ticket)
-        return out
+    # ---- end to end through the host-buffer C entries (lwop_infer_host_begin / _end) + host-side gather ----
+    # Frames start in pinned HOST memory as uint8 (what cv2.imread / VideoCapture hand the reference loop,
+    # model_test.py:59-65); every step every rank uploads its slice, runs `/ 255.` + forward + decode on the device and
+    # downloads its result tables straight into its region of a shared-memory ring; rank 0 reads the tables of ALL
+    # ranks of a step in image order (the host-side gather of SURVEY 8(e)) inside the timed region.  Up to `lanes`
+    # steps are in flight per rank, the way a serving loop drives the library.
+    ring_name = f"lwop_bench_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid())}"
+    ring = replicas.SharedResultRing(ring_name, G, world, rank, slots=lanes + 2)
+    n_host = lanes + 1
+    u8_host = [torch.from_numpy(np.ascontiguousarray(np.roll(frames_u8, k, 0))).pin_memory() for k in range(n_host)]
+    f32_host = [x_host] + [torch.roll(x_host, k, 0).pin_memory() for k in range(1, n_host)] if args.e2e_f32 else None
+    gathered = {"persons": 0, "images": 0}
+
+    def finish(st):
+        pool.result()
+        ring.publish(st)
+        if rank == 0:
+            views = ring.gather(st)
+            for v in views:              # consume: per-image person counts of every rank, in image order
+                gathered["persons"] += int(v["counts"][:v["batch"], 1].sum())
+                gathered["images"] += v["batch"]
+            ring.release(st)
+
+    def run_e2e(bufs, n):
+        pending = []
+        for _ in range(n):
+            st = seq.setdefault("e2e", 0)
+            seq["e2e"] = st + 1
+            if pool.in_flight == lanes:
+                finish(pending.pop(0))
+            ring.wait_slot_free(st)
+            pool.submit(bufs[st % len(bufs)], args.mode, PARAM["thre1"], PARAM["thre2"], tables=ring.tables(st))
+            pending.append(st)
+        while pending:
+            finish(pending.pop(0))
 
     def time_e2e(bufs):
-        run_e2e(bufs, max(2, min(args.warmup, 3)))
+        run_e2e(bufs, max(lanes + 1, min(args.warmup, 4)))
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run_e2e(bufs, args.steps)
+        pool.fork()
+        run_e2e(bufs, args.steps)        # returns after the last download has landed (and, on rank 0, the last gather)
         e1.record()
+        wall = 1e3 * (time.perf_counter() - t0)
         barrier()
-        return e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)     # device clock (ends after the last download)
+        return max(e0.elapsed_time(e1), wall), wall
 
-    e2e_ms, e2e_wall_ms = time_e2e([u8_a, u8_b])
-    d2h = eng.last_d2h_bytes
-    h2d = int(u8_a.numel())
-
-    # the same with float32 frames (the reference's `img / 255.` done on the host: 4x the upload) ...
-    e2e_f32_ms, _ = time_e2e([x_host])
-    # ... and one synchronous call per batch (no overlap across batches)
+    e2e_ms, e2e_wall_ms = time_e2e(u8_host)
+    d2h = eng0.last_d2h_bytes
+    h2d = int(u8_host[0].numel())
+    e2e_f32_ms = time_e2e(f32_host)[0] if args.e2e_f32 else 0.0
+    # one synchronous call per step (no overlap across steps)
     for _ in range(2):
-        eng.infer_host(u8_a, mode=args.mode)
+        eng0.infer_host(u8_host[0], mode=args.mode)
     barrier()
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.infer_host(u8_a, mode=args.mode)
-    es1.record()
+        eng0.infer_host(u8_host[0], mode=args.mode)
+    e2e_sync_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
-    e2e_sync_ms = es0.elapsed_time(es1)
-    e2e_u8_ms = e2e_f32_ms      # third slot of the cross-rank reduction below
 
-    # ---- max over ranks ----
-    t = torch.tensor([ms_total, e2e_ms, e2e_f32_ms, e2e_sync_ms], dtype=torch.float64, device="cuda")
+    # ---- max over ranks; totals over ranks ----
+    t = torch.tensor([ms_total, e2e_ms, e2e_f32_ms, e2e_sync_ms, ms_serial], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, e2e_f32_ms, e2e_sync_ms = (float(v) for v in t.cpu())
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, e2e_f32_ms, e2e_sync_ms, ms_serial = (float(v) for v in t.cpu())
+    launches, h2d, d2h = (int(v) for v in tot.cpu())
+    ring_bytes = ring.nbytes
+    ring.close()
 
     if rank == 0:
-        # ---- live per-kernel timing for the roofline (rank 0 only, outside the timed loops) ----
-        descs = eng.step_descs()
-        acc = np.zeros(len(descs))
-        n_prof = 5
-        eng.profile_forward(x_dev, mode=args.mode)
-        for _ in range(n_prof):
-            acc += np.asarray(eng.profile_forward(x_dev, mode=args.mode))
-        acc /= n_prof
-        classes = {}
-        for i, (d, ms) in enumerate(zip(descs, acc)):
-            cls = classify_step(d, descs[i + 1] if i + 1 < len(descs) else None)
-            if cls is None:
-                continue
-            c = classes.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-            fl, by = step_work(d, batch)
-            if d[9] == 2:        # fused: depthwise + pointwise flops; bytes = layer input + layer output only
-                fl2, _ = step_work(descs[i + 1], batch)
-                oh, ow = -(-d[2] // d[7]), -(-d[3] // d[7])
-                fl += fl2
-                by = 2.0 * (d[2] * d[3] * d[4] + oh * ow * descs[i + 1][5]) * batch
-            if d[9] == 4:        # fused head pair: flops of the four 1x1 convs; bytes = shared input + two narrow outputs
-                fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
-                by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
-            c["ms"] += ms
-            c["flops"] += fl
-            c["bytes"] += by
-            c["launches"] += 1
-        peaks = measured_peaks()
-        dom = max(classes, key=lambda k: classes[k]["ms"])
-        dc = classes[dom]
-        # a fused separable layer is bounded by whichever of the two rooflines is slower for its shape mix:
-        # report it against the tensor roofline when its tensor time exceeds its HBM time
-        tensor_bound = dom.startswith("gemm") or dom.startswith("head") or (dom.startswith("sep") and
-                                                  dc["flops"] / (peaks["bf16_tflops_sustained"] * 1e12) >
-                                                  dc["bytes"] / (peaks["hbm_gbs"] * 1e9))
-        if tensor_bound:
-            achieved = dc["flops"] / (dc["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
-        else:
-            achieved = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None}
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of the same workload
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-                tr = json.load(fh)
-            if tr.get("batch") == batch and dom in tr["traffic_bytes_per_launch"]:
-                roof["traffic"] = tr["traffic_bytes_per_launch"][dom]
-                roof["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, one launch)"
-                roof["algorithmic_bytes_per_launch"] = dc["bytes"] / dc["launches"]
-        except (OSError, ValueError, KeyError):
-            pass
-        roof["kernel"] = dom
-        roof["launches_per_step"] = dc["launches"]
-        roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
-        roof["peak_source"] = peaks["source"] + (" (sustained)" if tensor_bound else "")
-        per_class = {}
-        for k, c in classes.items():
-            per_class[k] = {"ms": round(c["ms"], 4), "launches": c["launches"],
-                            "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 2),
-                            "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)}
-        fwd_ms = float(acc.sum())
-        if args.dump_steps:
-            with open(args.dump_steps, "w") as fh:
-                for i, (d, ms) in enumerate(zip(descs, acc)):
-                    kind = classify_step(d, descs[i + 1] if i + 1 < len(descs) else None)
-                    if kind is None:
-                        continue
-                    fl, by = step_work(d, batch)
-                    if d[9] == 2:
-                        fl += step_work(descs[i + 1], batch)[0]
-                        by = 2.0 * (d[2] * d[3] * d[4] + d[2] * d[3] * descs[i + 1][5]) * batch
-                    if d[9] == 4:
-                        fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
-                        by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
-                    fh.write(json.dumps({"layer": d[0], "kind": kind, "in_hw": [d[2], d[3]], "cin": d[4],
-                                         "cout": descs[i + 1][5] if d[9] == 2 else d[5], "k": d[6], "stride": d[7], "dil": d[8], "ms": round(float(ms), 4),
-                                         "tflops": round(fl / (ms * 1e-3) / 1e12, 1),
-                                         "gbs": round(by / (ms * 1e-3) / 1e9, 1)}) + "\n")
-
+        roof, per_class, fwd_ms, peaks = roofline_record(eng0, x_devs[0], b, args.mode, args.dump_steps)
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 contract; cheap enough to always run) ----
         cpu = None
         if not args.no_cpu and world == 1:          # the CPU baseline is an N = 1 line (contract); skipped under torchrun
@@ -419,30 +546,47 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_images} synthetic 368x368 frames, batch-1 serial forward (torch-CPU fp32, "
                              f"{threads} threads) + decode (numpy/cv2, 1 thread), {dt:.1f} s"}
+        extras = {}
+        if world == 1 and not args.no_extras:
+            extras["latency_b1"] = latency_record(variables, source, local_rank, args.mode)
+            extras["configs3_656x368_20_person_scenes"] = dense_scene_record(variables, source, local_rank, args.mode,
+                                                                            0 if args.no_cpu else 4)
 
         ms_per_step = ms_total / args.steps
-        total_images = batch * world * args.steps
+        total_images = G * args.steps
         value = total_images / (ms_total * 1e-3)
+        step_tflops = GFLOP_TENSOR * G / ms_per_step / world        # per GPU, whole step (decode included in the time)
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": workload_name(batch, world),
-                "global_batch": batch * world, "height": H, "width": W, "mode": args.mode,
+                "workload": workload_name(G),
+                "global_batch": G, "frames_per_gpu_per_step": b, "height": H, "width": W, "mode": args.mode,
+                "steps_in_flight_per_gpu": lanes,
                 "weights": source, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
-                "l2": f"inputs {x_dev.numel() * 4 / 2**20:.0f} MiB fp32 per step > 126 MB L2 (no flush needed)",
+                "l2": f"each GPU cycles through {n_in} distinct float32 input buffers ({n_in * in_bytes / 2**20:.0f} MiB "
+                      "> 126 MB L2) and writes ~19 MB of activations per frame between two reads (no flush needed)",
                 "decode_load": {"joints_per_image": joints_per_img, "persons_per_image": persons_per_img},
+                "one_step_at_a_time": {"value": total_images / (ms_serial * 1e-3), "unit": "images/s",
+                                       "ms_per_step": ms_serial / args.steps},
                 "forward_ms_sum_of_kernels": round(fwd_ms, 3),
-                "forward_tflops_tensor": round(GFLOP_TENSOR * batch / fwd_ms, 1) if fwd_ms > 0 else None,
+                "forward_tflops_tensor": round(GFLOP_TENSOR * b / fwd_ms, 1) if fwd_ms > 0 else None,
+                "whole_step_tensor_frac": {"tflops_per_gpu": round(step_tflops, 1),
+                                           "of_sustained": round(step_tflops / peaks["bf16_tflops_sustained"], 4),
+                                           "of_burst": round(step_tflops / peaks["bf16_tflops"], 4)},
                 "kernel_classes": per_class,
                 "e2e_input": "uint8 frames in pinned host memory (the reference loop's frames before `/ 255.`), "
-                             "two batches in flight through lwop_infer_host_begin/_end",
-                "e2e_float32_frames": {"value": total_images / (e2e_f32_ms * 1e-3), "unit": "images/s",
-                                       "h2d_bytes_per_step": int(x_host.numel() * 4)},
-                "e2e_one_synchronous_call_per_batch": {"value": total_images / (e2e_sync_ms * 1e-3), "unit": "images/s"},
+                             f"{lanes} steps in flight per GPU through lwop_infer_host_begin/_end; result tables land in a "
+                             "shared-memory ring and rank 0 reads every rank's tables of each step in image order "
+                             "inside the timed region",
+                "e2e_gathered_on_rank0": {"images": gathered["images"], "persons": gathered["persons"],
+                                          "ring_bytes": ring_bytes},
+                "e2e_float32_frames": ({"value": total_images / (e2e_f32_ms * 1e-3), "unit": "images/s",
+                                        "h2d_bytes_per_step": G * H * W * 3 * 4} if args.e2e_f32 else None),
+                "e2e_one_synchronous_call_per_step": {"value": total_images / (e2e_sync_ms * 1e-3), "unit": "images/s"},
                 "e2e_wall_ms_per_step": e2e_wall_ms / args.steps,
-                "e2e_chunk_sweep_ms": sweep or None,
+                **extras,
             },
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -452,6 +596,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
         }
         print_json(json.dumps(line))
+    pool.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -477,14 +622,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="frames per step (ONE batch, sharded over the GPUs)")
+    ap.add_argument("--lanes", type=int, default=3, help="steps in flight per GPU (independent engines / CUDA streams)")
+    ap.add_argument("--e2e-f32", action="store_true", help="also time the host path with float32 frames (4x the upload)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency and the configs[3] sub-records")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
     ap.add_argument("--cpu-images", type=int, default=224,
                     help="frames in the bounded CPU-baseline sample (~11 s at ~20 images/s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="separable layers as two kernels (A/B timing of the fusion)")
-    ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage of the host-buffer path (0 = library default)")
-    ap.add_argument("--sweep-chunks", action="store_true", help="also time the host-buffer path for several chunk sizes")
     ap.add_argument("--dump-steps", default=None, help="write per-kernel timings (one JSON object per line) here")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -574,7 +574,7 @@ int forward_impl(lwop_handle *h, const FwdIO &io, int batch, int mode, cudaStrea
             break;
         }
     if (!gp) {
-        if (cache.size() >= 8) {            // callers cycling through many buffers: drop the oldest graph
+        if (cache.size() >= 32) {           // callers cycling through many buffers: drop the oldest graph
             if (cache.front().exec) cudaGraphExecDestroy(cache.front().exec);
             cache.erase(cache.begin());
         }

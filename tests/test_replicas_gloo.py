@@ -62,3 +62,49 @@ def test_two_gloo_ranks_match_single_process(tmp_path):
     want = np.array([r["joint_list"].shape[0] for r in single] + [np.asarray(r["persons"]).shape[0] for r in single])
     assert np.array_equal(np.load(out), want)
     assert np.array_equal(np.load(out + ".jl.npy"), np.concatenate([r["joint_list"].reshape(-1, 6) for r in single]))
+
+
+def _ring_worker(rank, world, port, name, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ring = replicas.SharedResultRing(name, N_SCENES, world, rank, slots=2, pin=False)
+        lo, hi = replicas.shard_bounds(N_SCENES, world, rank)
+        steps = 5                                   # more steps than slots: the slot hand-back is exercised
+        got = []
+        for step in range(steps):
+            scenes = [synth.synth_scene(900 + step * 10 + i, 1 + i % 3, 128, 128)[:2] for i in range(N_SCENES)]
+            ring.wait_slot_free(step)
+            replicas.pack_host_results(_decode_many(scenes[lo:hi]), ring._tables[step % ring.slots][rank])
+            ring.publish(step)
+            if rank == 0:
+                views = ring.gather(step)
+                res = [r for v in views for r in replicas.batch_result_from_tables(v)]
+                got.append(np.concatenate([r.joint_list.reshape(-1, 6) for r in res] +
+                                          [np.asarray(r.person_to_joint_assoc).reshape(-1, 16)[:, :6] for r in res]))
+                assert len(res) == N_SCENES
+                ring.release(step)
+        if rank == 0:
+            np.save(out_path, np.concatenate(got))
+        dist.barrier()
+        ring.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_memory_result_ring_two_ranks(tmp_path):
+    """The host-side gather of the batch-sharded job: two ranks write their packed result tables into one shared-memory
+    ring, rank 0 reads all of them in image order, 5 steps through 2 slots."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "ring.npy")
+    mp.spawn(_ring_worker, args=(2, port, f"lwop_test_ring_{port}", out), nprocs=2, join=True)
+    want = []
+    for step in range(5):
+        scenes = [synth.synth_scene(900 + step * 10 + i, 1 + i % 3, 128, 128)[:2] for i in range(N_SCENES)]
+        res = _decode_many(scenes)
+        want.append(np.concatenate([r["joint_list"].reshape(-1, 6) for r in res] +
+                                   [np.asarray(r["persons"]).reshape(-1, 16)[:, :6] for r in res]))
+    assert np.array_equal(np.load(out), np.concatenate(want))
