@@ -399,7 +399,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     b = hi - lo
     lanes = max(1, args.lanes)
     variables, source = checkpoint.load_or_synthesize()
-    pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank)
+    pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank, depth=args.depth)
     pool.load_variables(variables, source)
     eng0 = pool.engines[0]
 
@@ -469,38 +469,50 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ranks of a step in image order (the host-side gather of SURVEY 8(e)) inside the timed region.  Up to `lanes`
     # steps are in flight per rank, the way a serving loop drives the library.
     ring_name = f"lwop_bench_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid())}"
-    ring = replicas.SharedResultRing(ring_name, G, world, rank, slots=lanes + 2)
-    n_host = lanes + 1
+    ring = replicas.SharedResultRing(ring_name, G, world, rank, slots=pool.capacity + 2)
+    n_host = pool.capacity + 1
     u8_host = [torch.from_numpy(np.ascontiguousarray(np.roll(frames_u8, k, 0))).pin_memory() for k in range(n_host)]
     f32_host = [x_host] + [torch.roll(x_host, k, 0).pin_memory() for k in range(1, n_host)] if args.e2e_f32 else None
     gathered = {"persons": 0, "images": 0}
 
+    host_s = {"submit": 0.0, "wait_result": 0.0, "gather": 0.0, "slot": 0.0}     # host time per phase (BENCH_TRACE=1)
+
     def finish(st):
+        t0 = time.perf_counter()
         pool.result()
         ring.publish(st)
+        t1 = time.perf_counter()
         if rank == 0:
             views = ring.gather(st)
             for v in views:              # consume: per-image person counts of every rank, in image order
                 gathered["persons"] += int(v["counts"][:v["batch"], 1].sum())
                 gathered["images"] += v["batch"]
             ring.release(st)
+        host_s["wait_result"] += t1 - t0
+        host_s["gather"] += time.perf_counter() - t1
 
     def run_e2e(bufs, n):
         pending = []
         for _ in range(n):
             st = seq.setdefault("e2e", 0)
             seq["e2e"] = st + 1
-            if pool.in_flight == lanes:
+            if pool.in_flight == pool.capacity:
                 finish(pending.pop(0))
+            t0 = time.perf_counter()
             ring.wait_slot_free(st)
+            t1 = time.perf_counter()
             pool.submit(bufs[st % len(bufs)], args.mode, PARAM["thre1"], PARAM["thre2"], tables=ring.tables(st))
+            host_s["slot"] += t1 - t0
+            host_s["submit"] += time.perf_counter() - t1
             pending.append(st)
         while pending:
             finish(pending.pop(0))
 
     def time_e2e(bufs):
-        run_e2e(bufs, max(lanes + 1, min(args.warmup, 4)))
+        run_e2e(bufs, max(pool.capacity + 1, min(args.warmup, 4)))
         barrier()
+        for k in host_s:
+            host_s[k] = 0.0
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -512,6 +524,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         return max(e0.elapsed_time(e1), wall), wall
 
     e2e_ms, e2e_wall_ms = time_e2e(u8_host)
+    if os.environ.get("BENCH_TRACE") and rank == 0:
+        print("host ms per step:", {k: round(1e3 * v / args.steps, 4) for k, v in host_s.items()},
+              "wall ms per step:", round(e2e_wall_ms / args.steps, 4), file=sys.stderr)
     d2h = eng0.last_d2h_bytes
     h2d = int(u8_host[0].numel())
     e2e_f32_ms = time_e2e(f32_host)[0] if args.e2e_f32 else 0.0
@@ -563,7 +578,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "config": {
                 "workload": workload_name(G),
                 "global_batch": G, "frames_per_gpu_per_step": b, "height": H, "width": W, "mode": args.mode,
-                "steps_in_flight_per_gpu": lanes,
+                "steps_in_flight_per_gpu": lanes, "e2e_steps_in_flight_per_gpu": pool.capacity,
                 "weights": source, "thre1": PARAM["thre1"], "thre2": PARAM["thre2"],
                 "l2": f"each GPU cycles through {n_in} distinct float32 input buffers ({n_in * in_bytes / 2**20:.0f} MiB "
                       "> 126 MB L2) and writes ~19 MB of activations per frame between two reads (no flush needed)",
@@ -624,6 +639,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per step (ONE batch, sharded over the GPUs)")
     ap.add_argument("--lanes", type=int, default=3, help="steps in flight per GPU (independent engines / CUDA streams)")
+    ap.add_argument("--depth", type=int, default=1, help="host batches in flight per engine of the pool (1 or 2)")
     ap.add_argument("--e2e-f32", action="store_true", help="also time the host path with float32 frames (4x the upload)")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency and the configs[3] sub-records")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])

@@ -380,15 +380,21 @@ cudaError_t launch_u8_to_f32(const uint8_t *in, float *out, long long n, cudaStr
 // INTER_LINEAR fixed-point scheme: source position (d + 0.5) * scale - 0.5, 11-bit coefficients
 // saturate_cast<short>(f * 2048), horizontal pass in int32, vertical pass
 // (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.   One thread per output pixel.
+// The two axes differ at the border, as they do in OpenCV: along x an out-of-range source column becomes the border
+// column with the weight pair reset to (2048, 0); along y only the row indices are clipped and the fractional weight
+// pair is kept (the border row is blended with itself through two truncating products).
 // ---------------------------------------------------------------------------
+template <bool CLAMP_WEIGHTS>
 __device__ __forceinline__ void lin_taps(int d, double scale, int n, int &s0, int &s1, int &a0, int &a1) {
     float f = (float)((d + 0.5) * scale - 0.5);
     int s = (int)floorf(f);
     f -= (float)s;
-    if (s < 0) { s = 0; f = 0.0f; }
-    if (s >= n - 1) { s = n - 1; f = 0.0f; }
-    s0 = s;
-    s1 = min(s + 1, n - 1);
+    if (CLAMP_WEIGHTS) {
+        if (s < 0) { s = 0; f = 0.0f; }
+        if (s >= n - 1) { s = n - 1; f = 0.0f; }
+    }
+    s0 = min(max(s, 0), n - 1);
+    s1 = min(max(s + 1, 0), n - 1);
     a0 = (int)(short)__float2int_rn((1.0f - f) * 2048.0f);
     a1 = (int)(short)__float2int_rn(f * 2048.0f);
 }
@@ -401,8 +407,8 @@ __global__ void preprocess_bgr_kernel(const uint8_t *__restrict__ in, int B, int
     const int y = (int)((i / W) % H);
     const int b = (int)(i / ((long long)W * H));
     int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
-    lin_taps(x, scale_x, Ws, x0, x1, ax0, ax1);
-    lin_taps(y, scale_y, Hs, y0, y1, ay0, ay1);
+    lin_taps<true>(x, scale_x, Ws, x0, x1, ax0, ax1);
+    lin_taps<false>(y, scale_y, Hs, y0, y1, ay0, ay1);
     const uint8_t *r0 = in + ((long long)b * Hs + y0) * Ws * 3, *r1 = in + ((long long)b * Hs + y1) * Ws * 3;
     uint8_t *o = out + i * 3;
 #pragma unroll

@@ -504,12 +504,17 @@ class EnginePool:
     ``submit`` / ``result`` is the host-buffer path (upload, forward, decode, download per batch);
     ``step_device`` / ``join`` the device-resident one."""
 
-    def __init__(self, height: int, width: int, max_batch: int, lanes: int = 3, device: int = 0):
+    def __init__(self, height: int, width: int, max_batch: int, lanes: int = 3, device: int = 0, depth: int = 1):
+        """``depth``: host batches in flight per lane (1 or 2; with 2 the upload of a lane's next batch overlaps the
+        kernels of its current one inside the handle's two-slot pipeline)."""
         torch = _torch()
         require_gpu(device)
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
+        if depth not in (1, 2):
+            raise ValueError("depth must be 1 or 2")
         self.device = device
+        self.capacity = lanes * depth
         self.engines = [Engine(height, width, max_batch=max_batch, device=device,
                                stream=torch.cuda.Stream(device=device)) for _ in range(lanes)]
         self._next = 0
@@ -537,9 +542,9 @@ class EnginePool:
         return len(self._pending)
 
     def submit(self, images_host, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0, tables=None) -> None:
-        """Enqueue one batch of host frames on the next lane (at most one batch per lane in flight: call
-        :meth:`result` first when ``in_flight == len(pool)``)."""
-        if len(self._pending) >= len(self.engines):
+        """Enqueue one batch of host frames on the next lane (at most ``depth`` batches per lane in flight: call
+        :meth:`result` first when ``in_flight == pool.capacity``)."""
+        if len(self._pending) >= self.capacity:
             raise RuntimeError("every lane is busy: collect a result() first")
         lane = self._next
         self._next = (self._next + 1) % len(self.engines)
@@ -554,7 +559,7 @@ class EnginePool:
     def map(self, batches, mode: str = "bf16", thre1: float = 0.1, thre2: float = 0.0):
         """Generator over the results of an iterable of host batches, lanes kept full, submission order."""
         for images in batches:
-            if self.in_flight == len(self.engines):
+            if self.in_flight == self.capacity:
                 yield self.result()
             self.submit(images, mode, thre1, thre2)
         while self.in_flight:

@@ -23,8 +23,28 @@ def _frames(n, hw, seed):
     return out
 
 
+def test_device_preprocess_equals_cv2_golden_bytes():
+    """The CUDA pre-processing against bytes the installed cv2 produced (tests/golden/preprocess_golden.npz, IPP off;
+    up- and down-scaling, both axes): exact."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_golden.npz"))
+    k = 0
+    while f"frame{k}" in g:
+        frame, want = g[f"frame{k}"], g[f"rgb{k}"]
+        e = engine.Engine(want.shape[0], want.shape[1], max_batch=1, device=0, use_graph=False)
+        s = torch.from_numpy(frame[None]).cuda()
+        d = torch.empty((1,) + want.shape, dtype=torch.uint8, device="cuda")
+        _lib.check(e.lib.lwop_preprocess_bgr_u8(e.handle, s.data_ptr(), 1, frame.shape[0], frame.shape[1], d.data_ptr(),
+                                                want.shape[0], want.shape[1], torch.cuda.current_stream().cuda_stream),
+                   e.handle)
+        assert np.array_equal(d.cpu().numpy()[0], want), k
+        e.close()
+        k += 1
+    assert k >= 5
+
+
 @pytest.mark.parametrize("src,dst", [((480, 640), (256, 256)), ((720, 1280), (368, 368)), ((199, 301), (368, 656)),
-                                     ((368, 368), (368, 368))])
+                                     ((368, 368), (368, 368)), ((100, 100), (368, 368)), ((64, 48), (256, 256))])
 def test_device_preprocess_is_bit_exact_vs_oracle(src, dst):
     frames = np.stack(_frames(3, src, 11))
     e = engine.Engine(dst[0], dst[1], max_batch=3, device=0, use_graph=False)
