@@ -397,7 +397,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     G = args.batch                                   # ONE batch of G frames per step, sharded over the ranks
     lo, hi = replicas.shard_bounds(G, world, rank)
     b = hi - lo
-    lanes = max(1, args.lanes)
+    # steps in flight per GPU: small slices leave more of every kernel's fill / drain and of the latency-bound decode
+    # chain exposed, and more concurrent steps fill those gaps (measured: 3 lanes at 256 frames, 8 at 32)
+    lanes = args.lanes if args.lanes > 0 else max(3, min(8, 768 // b))
     variables, source = checkpoint.load_or_synthesize()
     pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank, depth=args.depth)
     pool.load_variables(variables, source)
@@ -638,8 +640,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per step (ONE batch, sharded over the GPUs)")
-    ap.add_argument("--lanes", type=int, default=3, help="steps in flight per GPU (independent engines / CUDA streams)")
-    ap.add_argument("--depth", type=int, default=1, help="host batches in flight per engine of the pool (1 or 2)")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="steps in flight per GPU (independent engines / CUDA streams); 0 = by slice size: 768 / frames, 3..8")
+    ap.add_argument("--depth", type=int, default=2, help="host batches in flight per engine of the pool (1 or 2)")
     ap.add_argument("--e2e-f32", action="store_true", help="also time the host path with float32 frames (4x the upload)")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency and the configs[3] sub-records")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16_direct"])
