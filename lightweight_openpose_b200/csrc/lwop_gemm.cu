@@ -43,6 +43,7 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
     int use_tma_store;              // wide bf16 output through shared-memory staging + TMA store
     unsigned park;                  // roles whose barrier waits park the warp (bit 0 TMA, 1 MMA, 3 epilogue), see mbar_wait_park
+    int B, tiles_x, tiles_y, num_tiles;   // halo kernel: 16 x 8 pixel tiles per image and in total
 };
 
 template <int BLOCK_N, int KSWZ, int STAGES, int MT>
@@ -589,6 +590,296 @@ gemm_conv2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Dense 3x3 convolution from ONE halo tile per K chunk (CTA pair, cta_group::2).
+// The im2col form above fetches every input pixel nine times (once per tap) from L2 and writes it nine times into
+// shared memory; this form loads the (16 + 2d) x (8 + 2d) pixel halo patch of a 16 x 8 output tile once per
+// 64-channel chunk (one 4D tiled TMA box, zero fill outside the map = 'same' padding) and addresses all nine taps as
+// SHIFTED VIEWS of that patch: with a tile 8 pixels wide the 128 MMA rows are 16 groups of 8 consecutive patch
+// pixels, so a K-major SWIZZLE_128B descriptor whose start address is moved by (r d (8 + 2d) + s d) 128-byte rows and
+// whose stride between 8-row groups (SBO) is the patch width (8 + 2d) * 128 bytes walks exactly the pixels tap
+// (r, s) needs.  The hardware applies the 128-byte swizzle to absolute shared-memory address bits, so any
+// 128-byte-aligned start row and any SBO are legal with base_offset = 0 (tools/ubench/desc_shift.cu).
+// Patch traffic L2 -> SM per output pixel: 1.41x (d = 1) / 1.88x (d = 2) instead of 9x; the price is spatial tiling:
+// 46 x 46 maps are covered by 3 x 6 tiles of 16 x 8 (8.9 % of the MMA rows fall outside the map and are clipped by
+// the TMA store).
+// Roles: warp 0 patch (A) producer, warp 3 weight (B) producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
+// allocation, warps 4-11 two epilogue groups.  Loop order per work item (MT tiles per CTA): chunk, tap, tile -- one
+// weight stage feeds the MMAs of both tiles.
+// ---------------------------------------------------------------------------
+template <int DIL, int MT, int SB>
+struct HaloSmem {
+    static constexpr int HW = 8 + 2 * DIL, HH = 16 + 2 * DIL;
+    static constexpr int kARows = HW * HH;
+    static constexpr int kATx = kARows * 128;                         // bytes one patch load delivers
+    static constexpr int kABytes = ((kATx + 1023) / 1024) * 1024;
+    static constexpr int SA = 2 * MT;                                 // patches of the current and the next chunk
+    static constexpr int kBBytes = 64 * 128;                          // this CTA's half of a [128 x 64] weight chunk
+    static constexpr int kBOffset = SA * kABytes;
+    static constexpr int kBarOffset = kBOffset + SB * kBBytes;
+    static constexpr int kNumBars = 2 * SA + 2 * SB + 4;
+    static constexpr int kBiasOffset = kBarOffset + ((kNumBars * 8 + 8 + 15) / 16) * 16;
+    static constexpr int kStagingOffset = ((kBiasOffset + 128 * 4 + 1023) / 1024) * 1024;
+    static constexpr int kTotal = kStagingOffset + 8 * 4096;
+    static_assert(kTotal <= 232448, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ void tma_load_4d_2sm(void *smem_dst, const void *desc, uint64_t *bar, int c0, int c1, int c2,
+                                                int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void *desc, const void *smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <int DIL, int MT, int SB>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+    using L = HaloSmem<DIL, MT, SB>;
+    constexpr int BLOCK_N = 128, SA = L::SA;
+    constexpr int kAccCols = MT * BLOCK_N;
+    constexpr uint32_t kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+    constexpr uint32_t kIdesc = make_idesc_bf16(256, BLOCK_N);        // M = 256 across the pair
+    constexpr uint32_t kSbo = L::HW * 128;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("lwop: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *a_empty = a_full + SA;
+    uint64_t *b_full = a_empty + SA;
+    uint64_t *b_empty = b_full + SB;
+    uint64_t *tmem_full = b_empty + SB;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + L::kBiasOffset);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int chunks = p.k_blocks_per_tap;                            // 64-channel chunks of Cin
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_items = (p.num_tiles + 2 * MT - 1) / (2 * MT);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_ptr);
+    for (int i = threadIdx.x; i < 128; i += kNumThreads) bias_s[i] = p.bias[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // tile t -> (image, first row, first column); tiles past the end name image B: every load is zero fill, every
+    // store is clipped
+    auto tile_origin = [&](int t, int &n, int &y0, int &x0) {
+        n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int ty = rem / p.tiles_x;
+        y0 = ty * 16;
+        x0 = (rem - ty * p.tiles_x) * 8;
+        if (t >= p.num_tiles) { n = p.B; y0 = 0; x0 = 0; }
+    };
+
+    if (warp == 0) {
+        // ===================== patch (A) producer: both CTAs, own tiles =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = pair_id; it < num_items; it += num_pairs) {
+                for (int c = 0; c < chunks; ++c) {
+#pragma unroll
+                    for (int hm = 0; hm < MT; ++hm) {
+                        int n, y0, x0;
+                        tile_origin((it * 2 + rank) * MT + hm, n, y0, x0);
+                        mbar_wait_sel(&a_empty[stage], phase ^ 1, p.park & 1u);
+                        if (leader) mbar_arrive_expect_tx(&a_full[stage], 2 * L::kATx);
+                        tma_load_4d_2sm(smem + stage * L::kABytes, &map_a, &a_full[stage], c * 64, x0 - DIL, y0 - DIL, n);
+                        if (++stage == SA) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight (B) producer: both CTAs, own half of the 128 output channels =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = pair_id; it < num_items; it += num_pairs) {
+                for (int c = 0; c < chunks; ++c) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait_sel(&b_empty[stage], phase ^ 1, p.park & 1u);
+                        if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * L::kBBytes);
+                        tma_load_2d_2sm(smem + L::kBOffset + stage * L::kBBytes, &map_b, &b_full[stage],
+                                        (tap * chunks + c) * 64, rank * 64);
+                        if (++stage == SB) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only, for the pair) =====================
+        if (leader) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int it = pair_id; it < num_items; it += num_pairs) {
+                mbar_wait_sel(&tmem_empty[acc], acc_phase ^ 1, p.park & 2u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
+                for (int c = 0; c < chunks; ++c) {
+                    // the MT patches of this chunk sit in stages sa .. sa + MT - 1 (SA is a multiple of MT)
+#pragma unroll
+                    for (int hm = 0; hm < MT; ++hm) mbar_wait_sel(&a_full[sa + hm], pa, p.park & 2u);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(smem + sa * L::kABytes);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait_sel(&b_full[sb], pb, p.park & 2u);
+                        tcgen05_fence_after();
+                        const int r = tap / 3, s = tap - r * 3;
+                        const uint32_t shift = (uint32_t)((r * DIL * L::HW + s * DIL) * 128);
+                        if (elect_one()) {
+                            const uint64_t db = make_kmajor_desc<128>(smem_u32(smem + L::kBOffset + sb * L::kBBytes));
+#pragma unroll
+                            for (int hm = 0; hm < MT; ++hm) {
+                                const uint64_t da = make_kmajor_desc_sbo(a0 + (uint32_t)(hm * L::kABytes) + shift, kSbo);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_ss_2sm(d_tmem + (uint32_t)(hm * BLOCK_N), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                                     kIdesc, (c | tap | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit_2sm(&b_empty[sb], 3);
+                            if (tap == 8) {
+#pragma unroll
+                                for (int hm = 0; hm < MT; ++hm) umma_commit_2sm(&a_empty[sa + hm], 3);
+                                if (c == chunks - 1) umma_commit_2sm(&tmem_full[acc], 3);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    sa += MT;
+                    if (sa == SA) { sa = 0; pa ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpilogueWarp0) {
+        // ===================== epilogue (both CTAs): warp q of a group owns tile rows 4q .. 4q + 3 =====================
+        const int q = (warp - kEpilogueWarp0) & 3;
+        const int grp = (warp - kEpilogueWarp0) >> 2;
+        const int acc = grp;
+        uint32_t acc_phase = 0;
+        unsigned char *stg = smem + L::kStagingOffset + (grp * 4 + q) * 4096;
+        int local = 0;
+        for (int it = pair_id; it < num_items; it += num_pairs, ++local) {
+            if ((local & 1) != grp) continue;
+            mbar_wait_sel(&tmem_full[acc], acc_phase, p.park & 8u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int hm = 0; hm < MT; ++hm) {
+                int n, y0, x0;
+                tile_origin((it * 2 + rank) * MT + hm, n, y0, x0);
+                const int y = y0 + q * 4 + (lane >> 3), x = x0 + (lane & 7);
+                const bool px_ok = n < p.B && y < p.H && x < p.W;
+                const long long m = ((long long)n * p.H + y) * p.W + x;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + hm * BLOCK_N);
+#pragma unroll 1
+                for (int g = 0; g < BLOCK_N / 64; ++g) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64), r0);
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + 32), r1);
+                    tmem_ld_wait();
+                    if (g == BLOCK_N / 64 - 1 && hm == MT - 1) {   // drained: hand the stage back to the leader's MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+                    }
+                    if (lane == 0) bulk_wait_read_all();
+                    __syncwarp();
+                    const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + g * 64);
+                    const uint4 *rp = (p.residual && px_ok)
+                                          ? reinterpret_cast<const uint4 *>(p.residual + m * p.ldr + g * 64)
+                                          : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v[8];
+                        const float4 b0 = bs4[2 * j], b1 = bs4[2 * j + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = j * 8 + e;
+                            const uint32_t raw = c < 32 ? r0[c] : r1[c - 32];
+                            v[e] = apply_act_fast(__uint_as_float(raw) + bb[e], p.act);
+                        }
+                        if (rp) {
+                            const uint4 rr = rp[j];
+                            v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                            v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4 *>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        // box (64 channels, 8 columns, 4 rows, 1 image); pixels outside the map are clipped
+                        tma_store_4d(&map_out, stg, p.out_col0 + g * 64, x0, y0 + q * 4, n);
+                        bulk_commit_group();
+                    }
+                }
+            }
+            acc_phase ^= 1;
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -674,6 +965,7 @@ struct GemmPlan {
     int cluster;
     int mt;
     int two_sm;        // CTA-pair (cta_group::2) kernel
+    int halo;          // dense 3x3 from one halo patch per chunk (conv3x3_halo_kernel), dilation = p.dil
     int grid;
     size_t smem;
 };
@@ -713,7 +1005,20 @@ cudaError_t launch_2sm(const GemmPlan *pl, cudaStream_t s) {
 }
 }  // namespace
 
+namespace {
+template <int DIL>
+cudaError_t launch_halo(const GemmPlan *pl, cudaStream_t s) {
+    constexpr int MT = 2, SB = 8;
+    auto kfn = conv3x3_halo_kernel<DIL, MT, SB>;
+    constexpr size_t smem = HaloSmem<DIL, MT, SB>::kTotal;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_chain(kfn, (unsigned)pl->grid, kNumThreads, smem, s, 2, pl->map_a, pl->map_b, pl->map_out, pl->p);
+}
+}  // namespace
+
 cudaError_t gemm_plan_launch(const GemmPlan *pl, cudaStream_t s, void *out_override, float *out2_override) {
+    if (pl->halo && !out_override && !out2_override) return pl->p.dil == 2 ? launch_halo<2>(pl, s) : launch_halo<1>(pl, s);
     if (pl->two_sm && !out_override && !out2_override) {
         if (pl->mt == 2) return pl->im2col ? launch_2sm<true, 4, 2>(pl, s) : launch_2sm<false, 4, 2>(pl, s);
         return pl->im2col ? launch_2sm<true, 7, 1>(pl, s) : launch_2sm<false, 7, 1>(pl, s);
@@ -831,10 +1136,29 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     const int work = ((p.num_m_tiles + pl->cluster - 1) / pl->cluster) * p.num_n_tiles;
     const int max_clusters = g_num_sms / pl->cluster;
     pl->grid = (work < max_clusters ? work : max_clusters) * pl->cluster;
+    // dense 3x3 from halo patches (LWOP_HALO=0 keeps the im2col form)
+    const char *eh = getenv("LWOP_HALO");
+    pl->halo = (pl->two_sm && im2col && (d.dil == 1 || d.dil == 2) && d.Cin_pad % 64 == 0 && !(eh && atoi(eh) == 0)) ? 1 : 0;
+    if (pl->halo) {
+        p.B = d.B;
+        p.tiles_x = (d.W + 7) / 8;
+        p.tiles_y = (d.H + 15) / 16;
+        p.num_tiles = d.B * p.tiles_x * p.tiles_y;
+        const int items = (p.num_tiles + 3) / 4;                    // MT = 2 tiles per CTA, two CTAs per item
+        pl->grid = (items < max_clusters ? items : max_clusters) * 2;
+    }
 
     const CUtensorMapSwizzle swz = kswz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r;
-    if (!im2col) {
+    if (pl->halo) {
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin_pad, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.W * d.lda * 2, (cuuint64_t)d.H * d.W * d.lda * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * d.dil), (cuuint32_t)(16 + 2 * d.dil), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = g_encode_tiled(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d.in), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (!im2col) {
         cuuint64_t dims[2] = {(cuuint64_t)d.Cin_pad, (cuuint64_t)M};
         cuuint64_t strides[1] = {(cuuint64_t)d.lda * 2};
         cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)kBlockM};
@@ -854,7 +1178,7 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    if (r == CUDA_SUCCESS && im2col) {
+    if (r == CUDA_SUCCESS && im2col && !pl->halo) {
         // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers up to
         // 13.1 mis-encode im2col maps of tensors smaller than 128 KiB; clear bit 21 of word 1.
         int drv = 0;
@@ -885,7 +1209,21 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     const bool wide = d.out_dtype == LWOP_DT_BF16 && d.Cout == d.Cout_pad && (d.out_col0 % 8) == 0 &&
                       (d.ldo % 8) == 0 && block_n >= 64 && d.out != nullptr && !getenv("LWOP_NO_TMA_STORE");
     p.use_tma_store = 0;
-    if (wide) {
+    if (pl->halo) {
+        cuuint64_t dims[4] = {(cuuint64_t)d.ldo, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+        cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 2, (cuuint64_t)d.W * d.ldo * 2, (cuuint64_t)d.H * d.W * d.ldo * 2};
+        cuuint32_t box[4] = {64, 8, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = g_encode_tiled(&pl->map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.out, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(err, errlen, "tensor map (out, halo) encode failed: CUresult %d", (int)r);
+            free(pl);
+            return nullptr;
+        }
+        p.use_tma_store = 1;
+    } else if (wide) {
         cuuint64_t dims[2] = {(cuuint64_t)d.ldo, (cuuint64_t)M};
         cuuint64_t strides[1] = {(cuuint64_t)d.ldo * 2};
         cuuint32_t box[2] = {64, 32};

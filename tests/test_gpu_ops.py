@@ -80,7 +80,17 @@ TC_CASES = [
     (1, 7, 5, 128, 128, 3, 1, 1, False, False),      # tiny tensor (< 128 KiB im2col map workaround)
     (40, 46, 46, 128, 128, 3, 1, 1, True, False),    # CTA-pair GEMM: several 512-row pair tiles per cluster, both TMEM stages
     (40, 46, 46, 512, 128, 1, 1, 1, False, False),   # CTA-pair GEMM, 1x1, deep K
+    (5, 46, 82, 128, 128, 3, 2, 1, True, False),     # halo-patch 3x3: wide map (656x368 frames), dilation 2, residual
+    (4, 17, 9, 128, 128, 3, 1, 2, False, False),     # halo-patch 3x3: 2 x 2 tiles per image, both clipped, ELU
+    (7, 46, 46, 128, 128, 3, 1, 0, False, False),    # halo-patch 3x3: tile count not a multiple of 4 (126), linear
 ]
+
+
+@pytest.mark.parametrize("case", [c for c in TC_CASES if c[5] == 3 and c[0] * c[1] * c[2] >= 512])
+def test_conv3x3_im2col_pair_kernel_still_works(eng, case, monkeypatch):
+    """LWOP_HALO=0 selects the im2col-mode TMA form of the dense 3x3 (the A/B switch of the halo-patch kernel)."""
+    monkeypatch.setenv("LWOP_HALO", "0")
+    test_conv_tcgen05_kernel(eng, case)
 
 
 @pytest.mark.parametrize("case", TC_CASES)
