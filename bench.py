@@ -195,7 +195,7 @@ def classify_step(desc, next_desc=None):
         return "depthwise3x3"
     if layer == 0:
         return "conv1_3x3s2"
-    return "gemm_conv3x3_im2col" if k == 3 else "gemm_conv1x1"
+    return "conv3x3_halo" if k == 3 else "gemm_conv1x1"
 
 
 def step_work(desc, batch):
@@ -236,10 +236,6 @@ def roofline_record(eng, x_dev, batch, mode, dump_steps=None):
         if d[9] == 4:        # fused head pair: flops of the four 1x1 convs; bytes = shared input + two narrow outputs
             fl = sum(step_work(descs[i + k], batch)[0] for k in range(4))
             by = (2.0 * d[4] + 4.0 * (descs[i + 1][5] + descs[i + 3][5])) * d[2] * d[3] * batch
-        if d[9] == 5:        # fused stem: first conv + depthwise + pointwise; bytes = frame in + 64-channel map out
-            fl = sum(step_work(descs[i + k], batch)[0] for k in range(3))
-            oh, ow = -(-d[2] // 2), -(-d[3] // 2)
-            by = (float(x_dev.element_size()) * d[2] * d[3] * 3 + 2.0 * oh * ow * descs[i + 2][5]) * batch
         c["ms"] += ms
         c["flops"] += fl
         c["bytes"] += by

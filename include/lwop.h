@@ -237,6 +237,14 @@ int lwop_conv2d(lwop_handle *h, int mode, const void *in_dev, int in_dtype,
                 const float *w_dev, const float *bias_dev, int cout, int ksize, int stride, int dilation,
                 int act, const void *residual_dev, void *out_dev, int out_dtype, void *stream);
 
+/* First layer alone: conv(inputs, 32, stride=2, bias=False) + folded batch norm + ReLU (lightweight_openpose.py:10,
+ * net_factory.py:4-12) in its production kernel (CUDA cores, packed fp32 FMA).  in_dev: NHWC frames, float32 in [0,1]
+ * or uint8 (in_is_u8: the `/ 255.` of model_test.py:65 runs inside the kernel); w_host float32 [32][27] (tap index
+ * (ky*3 + kx)*3 + c) and b_host float32 [32] in HOST memory (BN folded by the caller); out_dev bf16 NHWC
+ * [batch][ceil(H/2)][ceil(W/2)][32]. */
+int lwop_first_conv(lwop_handle *h, const void *in_dev, int in_is_u8, int batch, int height, int width,
+                    const float *w_host, const float *b_host, void *out_dev, void *stream);
+
 /* depthwise half of tf.layers.separable_conv2d (net_factory.py:15,25):
  * 3x3, channel multiplier 1, 'same', no bias, no activation.  w_dev float32 [9][C]. */
 int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype,

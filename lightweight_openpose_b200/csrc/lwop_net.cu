@@ -1240,6 +1240,18 @@ int lwop_conv2d(lwop_handle *h, int mode, const void *in_dev, int in_dtype, int 
     return rc;
 }
 
+int lwop_first_conv(lwop_handle *h, const void *in_dev, int in_is_u8, int batch, int height, int width,
+                    const float *w_host, const float *b_host, void *out_dev, void *stream) {
+    if (!h || !in_dev || !w_host || !b_host || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || height < 1 || width < 1) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    CU_OK(h, cudaSetDevice(h->device));
+    Conv1Weights cw;
+    CU_OK(h, conv1_pack_weights(w_host, b_host, &cw));
+    CU_OK(h, launch_conv1_bf16(cw, in_dev, in_is_u8, out_dev, batch, height, width, (cudaStream_t)stream));
+    h->launches++;
+    return LWOP_OK;
+}
+
 int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype, int batch, int height, int width,
                       int channels, const float *w_dev, int stride, int dilation, void *out_dev, void *stream) {
     if (!h || !in_dev || !w_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");

@@ -60,6 +60,35 @@ def test_conv_fp32_check_kernel(eng, case):
     assert np.abs(got - want).max() <= 2e-5
 
 
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("shape", [(2, 368, 368), (1, 37, 29), (3, 64, 50), (1, 368, 656), (2, 9, 7)])
+def test_first_conv_production_kernel(eng, shape, u8):
+    """conv1_bf16_kernel<float | uint8> (3 -> 32, stride 2, 'same' = pad 0 before / 1 after for even sizes) alone,
+    against float64 torch-CPU on the same inputs; output is bf16, so the bound is its rounding."""
+    B, H, W = shape
+    rng = np.random.default_rng(H * 31 + W + int(u8))
+    w = (rng.normal(size=(32, 27)) / np.sqrt(27.0)).astype(np.float32)
+    b = rng.normal(size=(32,)).astype(np.float32) * 0.1
+    if u8:
+        frames = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+        x = (frames / 255.).astype(np.float32)            # the kernel's LUT is float32(i / 255.)
+        xin = torch.from_numpy(frames).cuda()
+    else:
+        x = rng.random((B, H, W, 3), dtype=np.float32)
+        xin = torch.from_numpy(x).cuda()
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    out = torch.empty((B, Ho, Wo, 32), dtype=torch.bfloat16, device="cuda")
+    rc = eng.lib.lwop_first_conv(eng.handle, xin.data_ptr(), int(u8), B, H, W, w.ctypes.data_as(C.c_void_p),
+                                 b.ctypes.data_as(C.c_void_p), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, eng.handle)
+    torch.cuda.synchronize()
+    want = ref_conv_nhwc(x, w.reshape(32, 9, 3), b, 3, 2, 1, 1, None)
+    got = out.float().cpu().numpy()
+    err = np.abs(got - want)
+    tol = 2.0 ** -8 * max(1.0, float(np.abs(want).max())) + 1e-5
+    assert got.shape == want.shape and err.max() <= tol, (err.max(), tol)
+
+
 TC_CASES = [
     # B, H, W, cin, cout, k, dil, act, residual, out_f32
     (1, 16, 16, 64, 128, 1, 1, 1, False, False),     # one full M tile pair, K = 64

@@ -10,8 +10,14 @@ COMMON="--set full --clock-control none --import-source on --kernel-name-base de
 timeout 400 ncu $COMMON -k 'regex:sep_pair2_kernel<\(int\)1' -s 6 -c 1 -o $OUT/${TAG}_sep512 -f python tools/profile_forward.py 256 2 > $OUT/ncu_sep512.log 2>&1
 # fused separable, first layer (32 -> 64 at 184x184, HBM-bound)
 timeout 400 ncu $COMMON -k 'regex:sep_conv_kernel<\(int\)64' -s 1 -c 1 -o $OUT/${TAG}_sep32 -f python tools/profile_forward.py 256 2 > $OUT/ncu_sep32.log 2>&1
-# dense 3x3 128->128 (im2col, CTA-pair kernel): first of the 2nd forward
-timeout 400 ncu $COMMON -k 'regex:gemm_conv2sm_kernel<\(bool\)1' -s 14 -c 1 -o $OUT/${TAG}_conv3x3 -f python tools/profile_forward.py 256 2 > $OUT/ncu_c3.log 2>&1
+# dense 3x3 128->128 from halo patches (CTA-pair kernel), dilation 1 and 2: launches of the 2nd forward
+timeout 400 ncu $COMMON -k 'regex:conv3x3_halo_kernel<\(int\)1' -s 9 -c 1 -o $OUT/${TAG}_conv3x3_d1 -f python tools/profile_forward.py 256 2 > $OUT/ncu_c3d1.log 2>&1
+timeout 400 ncu $COMMON -k 'regex:conv3x3_halo_kernel<\(int\)2' -s 5 -c 1 -o $OUT/${TAG}_conv3x3_d2 -f python tools/profile_forward.py 256 2 > $OUT/ncu_c3d2.log 2>&1
 # fused head pair (initial stage, hidden 512)
 timeout 400 ncu $COMMON -k 'regex:head_pair_kernel' -s 2 -c 1 -o $OUT/${TAG}_heads -f python tools/profile_forward.py 256 2 > $OUT/ncu_heads.log 2>&1
+ls -la $OUT/${TAG}_*.ncu-rep
+# decode chain on the forward's own maps (batch 256): 2nd decode pass
+timeout 400 ncu $COMMON -k 'regex:peaks_kernel' -s 1 -c 1 -o $OUT/${TAG}_peaks -f python tools/profile_decode.py 256 > $OUT/ncu_peaks.log 2>&1
+timeout 400 ncu $COMMON -k 'regex:limbs_kernel' -s 1 -c 1 -o $OUT/${TAG}_limbs -f python tools/profile_decode.py 256 > $OUT/ncu_limbs.log 2>&1
+timeout 400 ncu $COMMON -k 'regex:group_fast_kernel' -s 1 -c 1 -o $OUT/${TAG}_group -f python tools/profile_decode.py 256 > $OUT/ncu_group.log 2>&1
 ls -la $OUT/${TAG}_*.ncu-rep
