@@ -307,6 +307,9 @@ bool step_fuses_with_next(const lwop_handle *h, size_t i) {
     const Step &s = h->steps[i], &n = h->steps[i + 1];
     if (!s.is_dw || n.is_dw || n.layer != s.layer || n.out_f32 || n.out2 >= 0) return false;
     const LayerSpec &l = kLayers[s.layer];
+    // LWOP_FUSE_ONLY=<layer>: debugging aid, fuse only this layer (bisecting a kernel problem by layer)
+    static const char *only = getenv("LWOP_FUSE_ONLY");
+    if (only && atoi(only) != s.layer) return false;
     return sep_plan_supported(l.cin, pad_cout(l.cout), l.stride, l.dil);
 }
 

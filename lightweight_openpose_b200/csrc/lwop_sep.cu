@@ -340,8 +340,12 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                             }
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
+                    // The slab is handed back to the TMA producer only AFTER the operand stores below: they consume every
+                    // accumulator, hence every load of the slab has returned its data by then.  Arriving right after the
+                    // loop is a write-after-read race -- nothing orders the barrier arrive (no register dependence) behind
+                    // shared-memory loads still in flight, and a refill that lands first feeds the last input rows of the
+                    // block with the NEXT chunk's pixels (seen as run-to-run differences in the layer with the slowest
+                    // epilogue, whose producer is always waiting for a free slab).
                     if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
                     PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));   // the MMAs that read this A stage retired
                     const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes);
@@ -352,8 +356,15 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                             asm volatile("st.shared.u32 [%0], %1;" ::"r"(abase + a_col[ox] + (uint32_t)(oy * kTW * 128)),
                                          "r"(pack_bf16x2(acc[oy][ox].x, acc[oy][ox].y))
                                          : "memory");
+                    // every writer makes ITS OWN generic-proxy stores visible to the async proxy (the tensor core reads the
+                    // operand through it) before the release; a fence on the consumer side alone is not enough -- it left
+                    // rare stale operand reads (1-2 images per 256 with 1e-3 differences from run to run)
+                    fence_proxy_async();
                     __syncwarp();                                          // orders the lanes' stores before lane 0's release
-                    if (lane == 0) mbar_arrive(&a_full[sa]);
+                    if (lane == 0) {
+                        mbar_arrive(&a_full[sa]);
+                        mbar_arrive(&slab_empty[ss]);                      // slab drained by this warp (see above)
+                    }
                     if (++ss == SS) { ss = 0; sph ^= 1; }
                     if (++sa == SA) { sa = 0; aph ^= 1; }
                 }
@@ -413,8 +424,6 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&slab_empty[ss]);          // slab drained by this warp
                 if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
                 PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));   // the MMAs that read this A stage retired
                 const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes) + a_off;
@@ -425,8 +434,12 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                                  "r"(hi)
                                  : "memory");
                 }
+                fence_proxy_async();                                   // writer-side proxy fence (see the 64-channel form above)
                 __syncwarp();                                          // orders the lanes' stores before lane 0's release
-                if (lane == 0) mbar_arrive(&a_full[sa]);
+                if (lane == 0) {
+                    mbar_arrive(&a_full[sa]);
+                    mbar_arrive(&slab_empty[ss]);                      // slab released after the stores that consumed it (see above)
+                }
                 if (++ss == SS) { ss = 0; sph ^= 1; }
                 if (++sa == SA) { sa = 0; aph ^= 1; }
             }
@@ -454,7 +467,11 @@ sep_conv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BLOCK_N);
             // residual rows (tf.add) are fetched one 32-column group ahead so their latency hides behind the previous group
-            const uint4 *rbase = (p.residual && row_ok) ? reinterpret_cast<const uint4 *>(p.residual + pix * p.ldr + n0) : nullptr;
+            // every lane reads a residual row (lanes outside the map read the clamped border pixel; their outputs are
+            // clipped by the TMA store): the loads stay warp-uniform, so the .sync.aligned tensor-memory loads below never
+            // run in a diverged warp
+            const size_t pixc = ((size_t)b * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
+            const uint4 *rbase = p.residual ? reinterpret_cast<const uint4 *>(p.residual + pixc * p.ldr + n0) : nullptr;
             uint4 rnext[4] = {};
             if (rbase) {
 #pragma unroll
@@ -877,8 +894,7 @@ sep_pair2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&slab_empty[ss]);
+                // (the slab is released after the operand stores that consume every load of it: see sep_conv_kernel)
                 if (pf) pf_acc[PF_DW_COMPUTE] += (unsigned long long)(clock64() - pf_c0);
                 PF_WAIT(PF_DW_AB_EMPTY, mbar_wait_sel(&a_empty[sa], aph ^ 1, p.park & 4u));
                 const uint32_t abase = smem_u32(smem + L::kAOff + sa * L::kABytes);
@@ -889,8 +905,12 @@ sep_pair2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(abase + a_col[ox] + (uint32_t)(oy * kTW * 128)),
                                      "r"(pack_bf16x2(acc[oy][ox].x, acc[oy][ox].y))
                                      : "memory");
+                fence_proxy_async();                   // writer-side proxy fence: own stores -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[sa]);
+                if (lane == 0) {
+                    mbar_arrive(&a_ready[sa]);
+                    mbar_arrive(&slab_empty[ss]);
+                }
                 if (++ss == SS) { ss = 0; sph ^= 1; }
                 if (++sa == SA) { sa = 0; aph ^= 1; }
             }

@@ -157,3 +157,19 @@ def test_async_host_path_matches_synchronous(variables):
         dev = eng.decode(heat, paf)
         for ra, rd in zip(a, dev):
             assert np.array_equal(ra.joint_list, rd.joint_list) and np.array_equal(ra.joints, rd.joints)
+
+
+def test_forward_is_bitwise_repeatable_over_many_replays(variables):
+    """40 graph replays of the same 64-frame batch: maps identical bit for bit (see the fused-separable regression test
+    in test_gpu_ops.py for the race this guards against)."""
+    eng = engine.Engine(368, 368, max_batch=64)
+    eng.load_variables(variables, "test")
+    x = torch.from_numpy(np.stack([synth.synth_image(s, 368, 368) for s in range(32)] * 2)).cuda()
+    heat, paf = eng.forward(x)
+    torch.cuda.synchronize()
+    h0, p0 = heat.clone(), paf.clone()
+    for run in range(40):
+        heat, paf = eng.forward(x)
+        torch.cuda.synchronize()
+        assert torch.equal(heat, h0) and torch.equal(paf, p0), f"replay {run} differs"
+    eng.close()
