@@ -219,9 +219,55 @@ def _crc_table() -> np.ndarray:
     return _CRC_TABLE
 
 
-def crc32c(data: bytes) -> int:
+_CRC_SLICES: Optional[np.ndarray] = None
+
+
+def _crc_slices() -> np.ndarray:
+    """Slice-by-8 tables: T[k][b] = CRC state after byte b followed by k zero bytes."""
+    global _CRC_SLICES
+    if _CRC_SLICES is None:
+        t0 = _crc_table().astype(np.uint64)
+        t = np.zeros((8, 256), dtype=np.uint64)
+        t[0] = t0
+        for k in range(1, 8):
+            t[k] = (t[k - 1] >> np.uint64(8)) ^ t0[(t[k - 1] & np.uint64(0xFF)).astype(np.int64)]
+        _CRC_SLICES = t
+    return _CRC_SLICES
+
+
+def _crc32c_native(data: bytes) -> Optional[int]:
+    """lwop_crc32c from the in-tree library when it is built (hardware-speed slice-by-8 in C)."""
+    try:
+        from . import _lib
+        import ctypes as C
+        lib = _lib.load()
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        return int(lib.lwop_crc32c(buf, len(data)))
+    except Exception:
+        return None
+
+
+def crc32c(data: bytes, native: bool = True) -> int:
+    """CRC32C of ``data``.  Uses the C implementation in ``_lwop.so`` when available (a 48 MB shard in well under a
+    second); otherwise a numpy slice-by-8 over 8-byte words (the per-byte Python loop took 0.6 s per MiB)."""
+    if native and len(data) >= 1024:
+        v = _crc32c_native(data)
+        if v is not None:
+            return v
     tbl = _crc_table()
     crc = 0xFFFFFFFF
+    n8 = len(data) // 8
+    if n8 >= 64:
+        t = _crc_slices()
+        words = np.frombuffer(data, dtype="<u8", count=n8)
+        # the CRC recurrence is sequential in the state, so the word loop stays in Python, but each step is 8 table
+        # look-ups on scalars instead of 8 interpreted byte iterations
+        tl = [t[k].tolist() for k in range(8)]
+        for w in words.tolist():
+            x = w ^ crc
+            crc = (tl[7][x & 0xFF] ^ tl[6][(x >> 8) & 0xFF] ^ tl[5][(x >> 16) & 0xFF] ^ tl[4][(x >> 24) & 0xFF] ^
+                   tl[3][(x >> 32) & 0xFF] ^ tl[2][(x >> 40) & 0xFF] ^ tl[1][(x >> 48) & 0xFF] ^ tl[0][(x >> 56) & 0xFF])
+        data = data[n8 * 8:]
     for b in data:
         crc = int(tbl[(crc ^ b) & 0xFF]) ^ (crc >> 8)
     return crc ^ 0xFFFFFFFF
@@ -245,6 +291,8 @@ def load_variables(prefix: str, verify_crc: bool = False,
     Raises FileNotFoundError if the data shard is missing (it is in the shipped
     reference: ``.MISSING_LARGE_BLOBS``)."""
     entries, header = read_index(prefix + ".index")
+    if header.get("endianness", 0) not in (0, None):
+        raise ValueError("big-endian TensorBundle shards are not supported")
     path = data_shard_path(prefix, 0, header["num_shards"])
     if not os.path.exists(path):
         raise FileNotFoundError(path)
@@ -253,6 +301,8 @@ def load_variables(prefix: str, verify_crc: bool = False,
         for name, e in entries.items():
             if only_inference and not is_inference_variable(name):
                 continue
+            if e.shard_id != 0:
+                raise ValueError(f"{name}: lives in shard {e.shard_id}; only single-shard bundles are supported")
             fh.seek(e.offset)
             raw = fh.read(e.size)
             if len(raw) != e.size:

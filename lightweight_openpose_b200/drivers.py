@@ -61,6 +61,10 @@ class PoseRunner:
         self.max_batch = max_batch
         self.engine = engine.Engine(self.H, self.W, max_batch=max_batch, device=device)
         self.weights_source = self.engine.load_checkpoint(checkpoint)
+        # network-size frames per batch size: the engine keys its CUDA graphs on the input pointer, so the staging
+        # tensor is owned here and reused (a fresh tensor per call would re-capture a graph whenever the allocator
+        # hands out a new address)
+        self._staging = {}
 
     def preprocess(self, frames_bgr: np.ndarray):
         """uint8 BGR ``[B, Hs, Ws, 3]`` (host) -> uint8 RGB ``[B, H, W, 3]`` CUDA tensor at the network size."""
@@ -71,7 +75,9 @@ class PoseRunner:
         B, Hs, Ws, _ = frames_bgr.shape
         dev = torch.device("cuda", self.device)
         src = torch.from_numpy(frames_bgr).to(dev, non_blocking=True)
-        dst = torch.empty((B, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+        dst = self._staging.get(B)
+        if dst is None:
+            dst = self._staging[B] = torch.empty((B, self.H, self.W, 3), dtype=torch.uint8, device=dev)
         e = self.engine
         _lib.check(e.lib.lwop_preprocess_bgr_u8(e.handle, src.data_ptr(), B, Hs, Ws, dst.data_ptr(), self.H, self.W,
                                                 e._stream()), e.handle)
@@ -88,9 +94,9 @@ class PoseRunner:
             for k in range(0, len(idx), self.max_batch):
                 part = idx[k:k + self.max_batch]
                 batch = np.stack([frames_bgr[i] for i in part])
-                rgb = self.preprocess(batch)
-                heat, paf = self.engine.forward(rgb)
-                res = self.engine.decode(heat, paf, (self.H, self.W), self.params["thre1"], self.params["thre2"])
+                rgb = self.preprocess(batch)            # valid until the next preprocess() of the same batch size
+                self.engine.forward_decode(rgb, "bf16", self.params["thre1"], self.params["thre2"])
+                res = self.engine.fetch(len(part))
                 frames_host = rgb.cpu().numpy() if keep_frames else None
                 for j, i in enumerate(part):
                     out[i] = FrameResult(res[j], frames_host[j] if keep_frames else None, (hs, ws))
