@@ -507,7 +507,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             finish(pending.pop(0))
 
     def time_e2e(bufs):
-        run_e2e(bufs, max(pool.capacity + 1, min(args.warmup, 4)))
+        # warm-up: every engine must have seen each of its (upload slot, result lane) pairs once -- each new pair captures
+        # a CUDA graph (eager pass + synchronisation), which must not happen inside the timed region
+        run_e2e(bufs, 2 * pool.capacity + 2)
         barrier()
         for k in host_s:
             host_s[k] = 0.0

@@ -8,6 +8,7 @@
 // match lwop_weights_num_floats() exactly.
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -107,6 +108,8 @@ struct GraphEntry {
 }  // namespace
 
 struct lwop_handle {
+    double host_us[6] = {0, 0, 0, 0, 0, 0};   // LWOP_TRACE_HOST=1: host time inside lwop_infer_host_begin by segment
+    long long host_calls = 0;
     int device = 0, max_batch = 0, H = 0, W = 0;
     unsigned flags = 0;
     int h2 = 0, w2 = 0, h4 = 0, w4 = 0, h8 = 0, w8 = 0;
@@ -740,6 +743,10 @@ int lwop_create(int device, int max_batch, int height, int width, unsigned flags
 }
 
 int lwop_destroy(lwop_handle *h) {
+    if (h && h->host_calls)
+        fprintf(stderr, "lwop host trace: %lld lwop_infer_host_begin calls, us per call: setup %.1f, upload+events %.1f, forward launch %.1f, "
+                        "pack+download+events %.1f\n", h->host_calls, h->host_us[0] / h->host_calls, h->host_us[1] / h->host_calls,
+                h->host_us[2] / h->host_calls, h->host_us[3] / h->host_calls);
     if (!h) return LWOP_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
@@ -1043,6 +1050,10 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
     for (int i = 0; i < LWOP_MAX_INFLIGHT; ++i)
         if (!h->lanes[i].busy) { lane = i; break; }
     if (lane < 0) return fail(h, LWOP_ERR_INVALID, "too many batches in flight: call lwop_infer_host_end first");
+    static const bool trace_host = getenv("LWOP_TRACE_HOST") != nullptr;
+    auto t_now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_seg = trace_host ? t_now() : 0.0;
+    auto seg = [&](int k) { if (trace_host) { const double t = t_now(); h->host_us[k] += t - t_seg; t_seg = t; } };
     cudaStream_t s = (cudaStream_t)stream;
     CU_OK(h, cudaSetDevice(h->device));
     // The batch is cut into chunks that flow through a two-slot pipeline: the copy stream uploads chunk
@@ -1085,18 +1096,24 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
     if (rc != LWOP_OK) return rc;
     const size_t esz = is_u8 ? 1 : 4;
     cudaStream_t ds = h->decode_stream;
+    seg(0);
     // chunk schedule: a half-size first chunk shortens the only upload that nothing can hide
     int k = 0;
     for (int b0 = 0, nb = 0; b0 < batch; b0 += nb, ++k) {
         nb = (k == 0 && batch > chunk && chunk >= 16) ? chunk / 2 : chunk;
         if (nb > batch - b0) nb = batch - b0;
-        const int slot = (int)(h->slot_seq++ & 1);                           // slots alternate ACROSS calls too
+        // The synchronous entry pipelines the chunks of ONE batch through the two slots (alternating across calls too);
+        // a batch submitted through the asynchronous entry goes through whole and takes the slot of its result lane, so
+        // that an engine only ever sees two (slot, lane) pairs -- each pair is a CUDA graph of its own, and with a free
+        // running slot counter a drained pipeline could restart on the two pairs it had never captured.
+        const int slot = lone_call ? (int)(h->slot_seq++ & 1) : lane;
         CU_OK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_fwd[slot], 0));   // previous frames in this slot consumed
         CU_OK(h, cudaStreamWaitEvent(s, h->ev_done[slot], 0));               // previous maps in this slot decoded
         CU_OK(h, cudaMemcpyAsync(h->slot_in[slot], (const char *)images_host + (size_t)b0 * img_elems * esz,
                                  (size_t)nb * img_elems * esz, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
         CU_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+        seg(1);
         // forward + decode chain: ONE graph launch on `s` (the decode kernels follow the last head kernel with
         // programmatic dependent launches); compaction and the downloads run on the decode stream behind it
         lwop_decode_tables t = ln.tables;
@@ -1113,6 +1130,7 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
         FwdIO io{h->slot_in[slot], is_u8, h->slot_heat[slot], h->slot_paf[slot], nullptr, nullptr, &a};
         rc = forward_impl(h, io, nb, mode, s);
         if (rc != LWOP_OK) return rc;
+        seg(2);
         CU_OK(h, cudaEventRecord(h->ev_fwd[slot], s));
         CU_OK(h, cudaStreamWaitEvent(ds, h->ev_fwd[slot], 0));
         if (heat_host)
@@ -1137,6 +1155,8 @@ int infer_host_begin_impl(lwop_handle *h, const void *images_host, int is_u8, in
         CU_OK(h, cudaMemcpyAsync(o->keypoints, ln.pk_keypoints, o->persons_cap * 42 * sizeof(float), cudaMemcpyDeviceToHost, ds));
     }
     CU_OK(h, cudaEventRecord(ln.ev_ready, ds));
+    seg(3);
+    if (trace_host) ++h->host_calls;
     // `s` deliberately does NOT wait for ev_ready: the next batch's forward may start while this batch is still
     // being decoded / downloaded on the decode stream (lwop_infer_host_end synchronises on ev_ready)
     ln.busy = true;

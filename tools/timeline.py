@@ -30,14 +30,15 @@ def main():
     lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     mode = sys.argv[3] if len(sys.argv) > 3 else "value"
     steps = int(sys.argv[4]) if len(sys.argv) > 4 else 9
+    depth = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     H = W = 368
     variables, src = checkpoint.load_or_synthesize()
-    pool = engine.EnginePool(H, W, max_batch=B, lanes=lanes)
+    pool = engine.EnginePool(H, W, max_batch=B, lanes=lanes, depth=depth)
     pool.load_variables(variables, src)
     base = np.stack([synth.synth_image(s, H, W) for s in range(32)])
     frames = np.concatenate([base] * (-(-B // 32)))[:B]
     xs = [torch.from_numpy(np.roll(frames, k, 0)).cuda() for k in range(lanes)]
-    hs = [torch.from_numpy(np.ascontiguousarray(np.roll(frames, k, 0))).pin_memory() for k in range(lanes + 1)]
+    hs = [torch.from_numpy(np.ascontiguousarray(np.roll(frames, k, 0))).pin_memory() for k in range(lanes * depth + 1)]
 
     def run(n):
         if mode == "value":
@@ -50,8 +51,8 @@ def main():
                 pass
         torch.cuda.synchronize()
 
-    run(2 * lanes)
-    run(2 * lanes)
+    run(2 * lanes * depth)
+    run(2 * lanes * depth)
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         run(steps)
     path = "/tmp/trace.json"
@@ -59,7 +60,7 @@ def main():
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
     ev.sort(key=lambda e: e["ts"])
     t0 = ev[0]["ts"]
-    out = f"gpurun_out/timeline_{mode}_b{B}_l{lanes}.csv"
+    out = f"gpurun_out/timeline_{mode}_b{B}_l{lanes}_d{depth}.csv"
     os.makedirs("gpurun_out", exist_ok=True)
     with open(out, "w") as fh:
         fh.write("start_us,dur_us,stream,name\n")
