@@ -43,7 +43,8 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region: NVML from a thread every ~2 ms (the timed region
+    of a sharded run lasts only tens of milliseconds), `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -51,8 +52,31 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ent = vis.split(",")[self.gpu].strip()
+                if ent.isdigit():
+                    idx = int(ent)
+                else:
+                    uuid = ent
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -62,11 +86,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                reasons = int(fn(self.handle))
+                self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            sm = [m for m, _ in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +138,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -499,7 +547,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             t0 = time.perf_counter()
             ring.wait_slot_free(st)
             t1 = time.perf_counter()
-            pool.submit(bufs[st % len(bufs)], args.mode, PARAM["thre1"], PARAM["thre2"], tables=ring.tables(st))
+            pool.submit(bufs[st % len(bufs)], args.mode, PARAM["thre1"], PARAM["thre2"],
+                        tables=None if os.environ.get("BENCH_NO_RING") else ring.tables(st))
             host_s["slot"] += t1 - t0
             host_s["submit"] += time.perf_counter() - t1
             pending.append(st)
