@@ -442,8 +442,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     lo, hi = replicas.shard_bounds(G, world, rank)
     b = hi - lo
     # steps in flight per GPU: small slices leave more of every kernel's fill / drain and of the latency-bound decode
-    # chain exposed, and more concurrent steps fill those gaps (measured: 3 lanes at 256 frames, 8 at 32)
-    lanes = args.lanes if args.lanes > 0 else max(3, min(8, 768 // b))
+    # chain exposed, and more concurrent steps fill those gaps (measured: 4 lanes at 256 frames, 16 at 32)
+    lanes = args.lanes if args.lanes > 0 else max(3, min(16, 1024 // b))
     variables, source = checkpoint.load_or_synthesize()
     pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank, depth=args.depth)
     pool.load_variables(variables, source)
@@ -688,7 +688,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per step (ONE batch, sharded over the GPUs)")
     ap.add_argument("--lanes", type=int, default=0,
-                    help="steps in flight per GPU (independent engines / CUDA streams); 0 = by slice size: 768 / frames, 3..8")
+                    help="steps in flight per GPU (independent engines / CUDA streams); 0 = by slice size: 1024 / frames, 3..16")
     ap.add_argument("--depth", type=int, default=2, help="host batches in flight per engine of the pool (1 or 2)")
     ap.add_argument("--e2e-f32", action="store_true", help="also time the host path with float32 frames (4x the upload)")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency and the configs[3] sub-records")
