@@ -1207,7 +1207,7 @@ GemmPlan *gemm_plan_create(const GemmConvDesc &d, char *err, size_t errlen) {
     }
     // wide bf16 outputs leave through shared-memory staging + TMA store (full 128-byte lines)
     const bool wide = d.out_dtype == LWOP_DT_BF16 && d.Cout == d.Cout_pad && (d.out_col0 % 8) == 0 &&
-                      (d.ldo % 8) == 0 && block_n >= 64 && d.out != nullptr && !getenv("LWOP_NO_TMA_STORE");
+                      (d.ldo % 8) == 0 && block_n >= 64 && d.out != nullptr;
     p.use_tma_store = 0;
     if (pl->halo) {
         cuuint64_t dims[4] = {(cuuint64_t)d.ldo, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
