@@ -367,6 +367,45 @@ def latency_record(variables, source, device, mode):
                     "forward + decode + download), and back-to-back device-resident forward+decode graph launches"}
 
 
+def batch64_forward_record(variables, source, device, check_frames: int):
+    """BASELINE.json configs[1]: batch 64, 368x368, forward only, bf16 and the fp32 check mode; the maps of the first
+    `check_frames` frames are compared with the CPU oracle (tolerances of BASELINE.json: 2e-2 bf16, 1e-4 fp32 check)."""
+    import torch
+    from lightweight_openpose_b200 import engine, synth
+    B = 64
+    eng = engine.Engine(H, W, max_batch=B, device=device)
+    eng.load_variables(variables, source)
+    frames = np.stack([synth.synth_image(s, H, W) for s in range(B)])
+    x = torch.from_numpy((frames / 255.).astype(np.float32)).cuda()
+    rec = {"batch": B, "height": H, "width": W}
+    outs = {}
+    for m, iters in (("bf16", 50), ("fp32", 3)):
+        for _ in range(3 if m == "bf16" else 1):
+            eng.forward(x, mode=m)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            heat, paf = eng.forward(x, mode=m)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        rec[f"{m}_images_per_s"] = B / (ms * 1e-3)
+        rec[f"{m}_ms_per_batch"] = round(ms, 4)
+        outs[m] = (heat[:check_frames].cpu().numpy().copy(), paf[:check_frames].cpu().numpy().copy())
+    eng.close()
+    if check_frames > 0:
+        from oracle.forward_oracle import ForwardOracle
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        oh, op = ForwardOracle(variables)((frames[:check_frames] / 255.).astype(np.float32))
+        for m in ("bf16", "fp32"):
+            rec[f"{m}_max_abs_err_vs_oracle"] = float(max(np.abs(outs[m][0] - oh).max(), np.abs(outs[m][1] - op).max()))
+        rec["checked_frames"] = check_frames
+        rec["tolerance"] = {"bf16": 2e-2, "fp32": 1e-4}
+    return rec
+
+
 def dense_scene_record(variables, source, device, mode, cpu_frames: int):
     """BASELINE.json configs[3]: 656x368 frames, 20-person scenes stressing the peak search and the grouping.
     decode-only: the scenes' heat maps / PAFs (label generator) fed to the decode chain; forward+decode:
@@ -613,6 +652,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         extras = {}
         if world == 1 and not args.no_extras:
             extras["latency_b1"] = latency_record(variables, source, local_rank, args.mode)
+            extras["configs1_batch64_forward_only"] = batch64_forward_record(variables, source, local_rank,
+                                                                               0 if args.no_cpu else 2)
             extras["configs3_656x368_20_person_scenes"] = dense_scene_record(variables, source, local_rank, args.mode,
                                                                             0 if args.no_cpu else 4)
 
