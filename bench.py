@@ -553,7 +553,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # downloads its result tables straight into its region of a shared-memory ring; rank 0 reads the tables of ALL
     # ranks of a step in image order (the host-side gather of SURVEY 8(e)) inside the timed region.  Up to `lanes`
     # steps are in flight per rank, the way a serving loop drives the library.
-    ring_name = f"lwop_bench_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid())}"
+    # segment name: a token drawn by rank 0 and broadcast, so that no rank can attach to a stale segment of an earlier
+    # (crashed) run that used the same rendezvous port
+    tok = torch.tensor([int.from_bytes(os.urandom(6), "little")], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.broadcast(tok, src=0)
+    ring_name = f"lwop_bench_{int(tok.item()):x}"
     ring = replicas.SharedResultRing(ring_name, G, world, rank, slots=pool.capacity + 2)
     n_host = pool.capacity + 1
     u8_host = [torch.from_numpy(np.ascontiguousarray(np.roll(frames_u8, k, 0))).pin_memory() for k in range(n_host)]
