@@ -483,8 +483,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # steps in flight per GPU: small slices leave more of every kernel's fill / drain and of the latency-bound decode
     # chain exposed, and more concurrent steps fill those gaps (measured: 4 lanes at 256 frames, 16 at 32)
     lanes = args.lanes if args.lanes > 0 else max(3, min(16, 1024 // b))
+    # the result ring lives in /dev/shm (~16 kB per frame and slot): fall back to a shallow pipeline on a box whose
+    # tmpfs could not hold it
+    depth = args.depth
+    try:
+        st = os.statvfs("/dev/shm")
+        if (lanes * depth + 2) * G * 16500 * 2 > st.f_bavail * st.f_frsize:
+            lanes, depth = min(lanes, 4), 1
+    except OSError:
+        pass
     variables, source = checkpoint.load_or_synthesize()
-    pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank, depth=args.depth)
+    pool = engine.EnginePool(H, W, max_batch=b, lanes=lanes, device=local_rank, depth=depth)
     pool.load_variables(variables, source)
     eng0 = pool.engines[0]
 
