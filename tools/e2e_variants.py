@@ -21,7 +21,8 @@ def val(n):
         pool.step_device(xs[i % L])
     pool.join()
     torch.cuda.synchronize()
-for fn, name in ((e2e, "e2e pool.map"), (val, "value")):
+order = ((val, "value"), (e2e, "e2e pool.map"), (val, "value again")) if os.environ.get("VALUE_FIRST") else ((e2e, "e2e pool.map"), (val, "value"))
+for fn, name in order:
     fn(4 * L * D)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
