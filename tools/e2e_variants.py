@@ -12,6 +12,8 @@ base = np.stack([synth.synth_image(s, 368, 368) for s in range(32)])
 nh = int(sys.argv[3]) if len(sys.argv) > 3 else L * D + 1
 hs = [torch.from_numpy(np.ascontiguousarray(np.roll(base, k, 0))).pin_memory() for k in range(nh)]
 xs = [torch.from_numpy((np.roll(base, k, 0) / 255.).astype(np.float32)).cuda() for k in range(L)]
+if os.environ.get("VALUE_U8"):
+    xs = [torch.from_numpy(np.ascontiguousarray(np.roll(base, k, 0))).cuda() for k in range(L)]
 def e2e(n):
     for _ in pool.map(hs[i % nh] for i in range(n)):
         pass
