@@ -21,3 +21,8 @@ timeout 400 ncu $COMMON -k 'regex:peaks_kernel' -s 1 -c 1 -o $OUT/${TAG}_peaks -
 timeout 400 ncu $COMMON -k 'regex:limbs_kernel' -s 1 -c 1 -o $OUT/${TAG}_limbs -f python tools/profile_decode.py 256 > $OUT/ncu_limbs.log 2>&1
 timeout 400 ncu $COMMON -k 'regex:group_fast_kernel' -s 1 -c 1 -o $OUT/${TAG}_group -f python tools/profile_decode.py 256 > $OUT/ncu_group.log 2>&1
 ls -la $OUT/${TAG}_*.ncu-rep
+# the remaining kernel classes: first conv, stride-2 depthwise, 128-wide 1x1 GEMM (CTA pair)
+timeout 400 ncu $COMMON -k 'regex:conv1_bf16_kernel' -s 1 -c 1 -o $OUT/${TAG}_conv1 -f python tools/profile_forward.py 256 2 > $OUT/ncu_conv1.log 2>&1
+timeout 400 ncu $COMMON -k 'regex:dw_tma_kernel' -s 2 -c 1 -o $OUT/${TAG}_dw -f python tools/profile_forward.py 256 2 > $OUT/ncu_dw.log 2>&1
+timeout 400 ncu $COMMON -k 'regex:gemm_conv2sm_kernel<\(bool\)0' -s 8 -c 1 -o $OUT/${TAG}_gemm1x1 -f python tools/profile_forward.py 256 2 > $OUT/ncu_gemm1x1.log 2>&1
+ls -la $OUT/${TAG}_*.ncu-rep | wc -l
