@@ -37,7 +37,7 @@ def test_forward_fp32_check_mode(variables, hw, batch):
 
 
 @pytest.mark.parametrize("mode", ["bf16_direct", "bf16"])
-@pytest.mark.parametrize("hw,batch", [((368, 368), 2), ((368, 656), 1), ((256, 256), 3)])
+@pytest.mark.parametrize("hw,batch", [((368, 368), 2), ((368, 656), 1), ((256, 256), 3), ((250, 362), 2), ((136, 72), 5)])
 def test_forward_bf16(variables, hw, batch, mode):
     x = synth.synth_batch(range(10, 10 + batch), hw[0], hw[1])
     oh, op, oh1, op1 = ForwardOracle(variables)(x, return_stage1=True)
