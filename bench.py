@@ -322,6 +322,21 @@ def roofline_record(eng, x_dev, batch, mode, dump_steps=None):
             roof["algorithmic_bytes_per_launch"] = dc["bytes"] / dc["launches"]
     except (OSError, ValueError, KeyError):
         pass
+    # the same figure for every kernel class (which roofline bounds a class: tensor when its tensor time at the sustained
+    # peak exceeds its HBM time at the copy bandwidth)
+    per_class_roof = {}
+    for k, c in classes.items():
+        t_tensor = c["flops"] / (peaks["bf16_tflops_sustained"] * 1e12)
+        t_hbm = c["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        tb = k.startswith(("gemm_conv3", "conv3x3", "head")) or (not k.startswith(("conv1", "depthwise")) and t_tensor > t_hbm)
+        if tb:
+            a = c["flops"] / (c["ms"] * 1e-3) / 1e12
+            per_class_roof[k] = {"bound": "tensor", "achieved_tflops": round(a, 1), "frac": round(a / peaks["bf16_tflops_sustained"], 3),
+                                 "frac_burst": round(a / peaks["bf16_tflops"], 3), "ms": round(c["ms"], 4)}
+        else:
+            a = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            per_class_roof[k] = {"bound": "hbm", "achieved_gbs": round(a, 1), "frac": round(a / peaks["hbm_gbs"], 3), "ms": round(c["ms"], 4)}
+    roof["classes"] = per_class_roof
     roof["kernel"] = dom
     roof["launches_per_step"] = dc["launches"]
     roof["avg_launch_ms"] = dc["ms"] / dc["launches"]
