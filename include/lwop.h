@@ -179,6 +179,15 @@ int lwop_find_connected_joints(lwop_handle *h, const float *paf_dev, int paf_ups
 int lwop_group_limbs(lwop_handle *h, const float *peaks_dev, const int32_t *peak_counts_dev, int batch,
                      const lwop_decode_tables *tables_dev, void *stream);
 
+/* Drawing half of plot_pose (src/pose_decode.py:431-436) on the device: for every person of `tables_dev` (in table
+ * order) and limb type (in order) whose two joints are set, two filled white circles of radius 3 and a line of
+ * thickness 2 in colors[person % 16] (:26-31), painted in the reference's order onto a copy of the frame.  The pixel
+ * sets are those of cv2.circle / cv2.line (OpenCV 4.x, LINE_8), so the canvas is byte-identical to the reference's.
+ * img_dev, canvas_dev: uint8 [batch][img_h][img_w][3] (canvas_dev may be img_dev: draw in place); reads counts[b][1],
+ * joints and persons of tables_dev (lwop_decode / lwop_forward_decode / lwop_group_limbs output). */
+int lwop_draw_poses(lwop_handle *h, const uint8_t *img_dev, int batch, int img_h, int img_w,
+                    const lwop_decode_tables *tables_dev, uint8_t *canvas_dev, void *stream);
+
 /* Host-side result of lwop_infer_host / lwop_decode_fetch: rows of all images
  * concatenated in image order (per image: counts[b][0] joint rows, counts[b][1]
  * person / keypoint rows, counts[b][18+t] limb rows per limb type t in order). */

@@ -66,6 +66,7 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_nms": (_i, [_vp, _vp, _i, _i, _i, _d, _f, _i, _vp, _vp, _vp, _vp]),
     "lwop_find_connected_joints": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "lwop_group_limbs": (_i, [_vp, _vp, _vp, _i, C.POINTER(DecodeTables), _vp]),
+    "lwop_draw_poses": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(DecodeTables), _vp, _vp]),
     "lwop_decode_fetch": (_i, [_vp, C.POINTER(DecodeTables), _i, C.POINTER(PackedTables), _vp]),
     "lwop_infer_host": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp]),
     "lwop_infer_host_begin": (_i, [_vp, _vp, _i, _i, _i, _f, _d, C.POINTER(PackedTables), _vp, _vp, _vp, C.POINTER(_i)]),

@@ -150,6 +150,11 @@ void head_pair_plan_destroy(HeadPairPlan *p);
 cudaError_t head_pair_plan_launch(const HeadPairPlan *p, cudaStream_t s, float *out_a_override = nullptr,
                                   float *out_b_override = nullptr);
 
+// lwop_draw.cu -- drawing half of plot_pose (circles + thick lines, OpenCV's pixel sets) through a priority map
+// prio: int32 [B][H][W], all -1 on entry and again on exit
+cudaError_t launch_draw_poses(const uint8_t *img, int B, int H, int W, const int *counts, const double *joints,
+                              const double *persons, int *prio, uint8_t *canvas, cudaStream_t s, long long *launches);
+
 // lwop_decode.cu
 struct DecodeArgs {
     const float *heat;   // [B,h,w,14]

@@ -138,6 +138,8 @@ struct lwop_handle {
     int *peak_counts = nullptr;
     double *group_work = nullptr;
     int *pack_offsets = nullptr;
+    int *draw_prio = nullptr;                    // canvas rasteriser: priority map [pixels], -1 between calls
+    size_t draw_prio_cap = 0;
     double *pk_joints = nullptr, *pk_limbs = nullptr, *pk_persons = nullptr;
     float *pk_keypoints = nullptr;
     size_t pk_joints_cap = 0, pk_limbs_cap = 0, pk_persons_cap = 0;
@@ -765,6 +767,7 @@ int lwop_destroy(lwop_handle *h) {
     if (h->peak_counts) cudaFree(h->peak_counts);
     if (h->group_work) cudaFree(h->group_work);
     if (h->pack_offsets) cudaFree(h->pack_offsets);
+    if (h->draw_prio) cudaFree(h->draw_prio);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
     if (h->pk_joints) cudaFree(h->pk_joints);
     if (h->pk_limbs) cudaFree(h->pk_limbs);
@@ -871,6 +874,29 @@ int lwop_preprocess_bgr_u8(lwop_handle *h, const uint8_t *in_dev, int batch, int
     CU_OK(h, cudaSetDevice(h->device));
     CU_OK(h, launch_preprocess_bgr(in_dev, batch, src_h, src_w, out_dev, dst_h, dst_w, (cudaStream_t)stream));
     h->launches++;
+    return LWOP_OK;
+}
+
+int lwop_draw_poses(lwop_handle *h, const uint8_t *img_dev, int batch, int img_h, int img_w,
+                    const lwop_decode_tables *t, uint8_t *canvas_dev, void *stream) {
+    if (!h || !img_dev || !canvas_dev || !t || !t->counts || !t->joints || !t->persons)
+        return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (batch < 1 || img_h < 1 || img_w < 1) return fail(h, LWOP_ERR_INVALID, "bad geometry");
+    if (img_h > 16384 || img_w > 16384) return fail(h, LWOP_ERR_UNSUPPORTED, "frame larger than 16384 pixels per side");
+    CU_OK(h, cudaSetDevice(h->device));
+    const size_t pixels = (size_t)batch * img_h * img_w;
+    if (pixels > h->draw_prio_cap) {
+        // the map is all -1 between calls (the resolve pass resets what the mark pass touched); a new one starts so
+        CU_OK(h, cudaStreamSynchronize((cudaStream_t)stream));
+        if (h->draw_prio) cudaFree(h->draw_prio);
+        h->draw_prio = nullptr;
+        h->draw_prio_cap = 0;
+        CU_OK(h, cudaMalloc(&h->draw_prio, pixels * sizeof(int)));
+        h->draw_prio_cap = pixels;
+        CU_OK(h, cudaMemsetAsync(h->draw_prio, 0xFF, pixels * sizeof(int), (cudaStream_t)stream));
+    }
+    CU_OK(h, launch_draw_poses(img_dev, batch, img_h, img_w, t->counts, t->joints, t->persons, h->draw_prio, canvas_dev,
+                               (cudaStream_t)stream, &h->launches));
     return LWOP_OK;
 }
 

@@ -9,7 +9,9 @@
 
 Here the frames of a batch are uploaded as uint8 BGR (4x less PCIe traffic than float32), and colour swap, resize,
 ``/ 255.``, the network and the decode all run on the GPU; only the small result tables come back.  The canvas
-(``plot_pose`` drawing) is produced on request on the host, as in ``pose_decode.decode_pose``.
+(``plot_pose`` drawing) is produced on request: on the host with cv2 from the kept frame (``keep_frames=True``), as in
+``pose_decode.decode_pose``, or by the CUDA rasteriser straight from the device-resident result tables
+(``draw=True``; the same bytes).
 """
 from __future__ import annotations
 
@@ -32,19 +34,24 @@ def _torch():
 
 class FrameResult:
     """What one iteration of the reference loop produces (model_test.py:68-71)."""
-    __slots__ = ("joint_list", "person_to_joint_assoc", "joints", "img_data", "orig_hw")
+    __slots__ = ("joint_list", "person_to_joint_assoc", "joints", "img_data", "orig_hw", "canvas_data")
 
-    def __init__(self, res: "engine.DecodeResult", img_data: Optional[np.ndarray], orig_hw: Tuple[int, int]):
+    def __init__(self, res: "engine.DecodeResult", img_data: Optional[np.ndarray], orig_hw: Tuple[int, int],
+                 canvas_data: Optional[np.ndarray] = None):
         self.joint_list = res.joint_list
         self.person_to_joint_assoc = res.person_to_joint_assoc
         self.joints = res.joints
         self.img_data = img_data            # resized RGB uint8 frame (only when requested)
         self.orig_hw = orig_hw
+        self.canvas_data = canvas_data      # canvas rasterised on the device (only with draw=True)
 
     def canvas(self) -> np.ndarray:
-        """The drawn frame of ``plot_pose`` (pose_decode.py:431-436); needs ``keep_frames=True``."""
+        """The drawn frame of ``plot_pose`` (pose_decode.py:431-436); needs ``draw=True`` (drawn on the device) or
+        ``keep_frames=True`` (drawn here with cv2)."""
+        if self.canvas_data is not None:
+            return self.canvas_data
         if self.img_data is None:
-            raise ValueError("run with keep_frames=True to get canvases")
+            raise ValueError("run with draw=True or keep_frames=True to get canvases")
         if not self.person_to_joint_assoc.size:
             return self.img_data.copy()
         return pose_decode.plot_pose(self.img_data, self.joint_list, self.person_to_joint_assoc)[0]
@@ -83,9 +90,10 @@ class PoseRunner:
                                                 e._stream()), e.handle)
         return dst
 
-    def run_frames(self, frames_bgr: Sequence[np.ndarray], keep_frames: bool = False) -> List[FrameResult]:
+    def run_frames(self, frames_bgr: Sequence[np.ndarray], keep_frames: bool = False, draw: bool = False) -> List[FrameResult]:
         """``frames_bgr``: uint8 BGR frames as ``cv2.imread`` / ``VideoCapture.read`` return them (any sizes).
-        Frames of equal size are batched together; results come back in input order."""
+        Frames of equal size are batched together; results come back in input order.  ``draw=True`` rasterises the
+        canvases of ``plot_pose`` on the device from the decode tables (``lwop_draw_poses``) and downloads them."""
         out: List[Optional[FrameResult]] = [None] * len(frames_bgr)
         by_size: Dict[Tuple[int, int], List[int]] = {}
         for i, f in enumerate(frames_bgr):
@@ -96,10 +104,12 @@ class PoseRunner:
                 batch = np.stack([frames_bgr[i] for i in part])
                 rgb = self.preprocess(batch)            # valid until the next preprocess() of the same batch size
                 self.engine.forward_decode(rgb, "bf16", self.params["thre1"], self.params["thre2"])
+                canvases = self.engine.draw_poses(rgb).cpu().numpy() if draw else None
                 res = self.engine.fetch(len(part))
                 frames_host = rgb.cpu().numpy() if keep_frames else None
                 for j, i in enumerate(part):
-                    out[i] = FrameResult(res[j], frames_host[j] if keep_frames else None, (hs, ws))
+                    out[i] = FrameResult(res[j], frames_host[j] if keep_frames else None, (hs, ws),
+                                         canvases[j] if draw else None)
         return out            # type: ignore[return-value]
 
 

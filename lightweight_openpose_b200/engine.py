@@ -318,6 +318,37 @@ class Engine:
                                                 paf.data_ptr(), C.byref(s), self._stream()), self.handle)
         return heat, paf
 
+    def draw_poses(self, frames, tables=None, out=None):
+        """Canvases of ``plot_pose`` (reference pose_decode.py:431-436) drawn on the device: ``frames`` uint8 CUDA
+        ``[B,H,W,3]`` (any H, W); ``tables`` = dict of device tables (``counts``, ``joints``, ``persons``; default: the
+        engine's own, i.e. the result of the last :meth:`decode_device` / :meth:`forward_decode`).  Returns a new uint8
+        tensor (or ``out``, which may be ``frames`` itself), byte-identical to cv2's drawing."""
+        torch = _torch()
+        if frames.device.type != "cuda" or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 \
+                or not frames.is_contiguous():
+            raise ValueError("frames must be a contiguous uint8 CUDA tensor [B,H,W,3]")
+        B, H, W, _ = frames.shape
+        if tables is None:
+            if B > self.max_batch:
+                raise ValueError("batch exceeds engine capacity")
+            _, s = self._device_tables()
+        else:
+            for k, dt, tail in (("counts", torch.int32, (_lib.COUNTS,)), ("joints", torch.float64, (_lib.MAX_JOINTS, 6)),
+                                ("persons", torch.float64, (_lib.MAX_PERSONS, 16))):
+                t = tables[k]
+                if t.device != frames.device or t.dtype != dt or tuple(t.shape[1:]) != tail or t.shape[0] < B \
+                        or not t.is_contiguous():
+                    raise ValueError(f"tables['{k}'] must be a contiguous {dt} CUDA tensor [>= {B}, {tail}]")
+            s = _lib.DecodeTables(tables["counts"].data_ptr(), tables["joints"].data_ptr(), None,
+                                  tables["persons"].data_ptr(), None)
+        if out is None:
+            out = torch.empty_like(frames)
+        elif out.shape != frames.shape or out.dtype != torch.uint8 or out.device != frames.device or not out.is_contiguous():
+            raise ValueError("out must match frames")
+        _lib.check(self.lib.lwop_draw_poses(self.handle, frames.data_ptr(), B, H, W, C.byref(s), out.data_ptr(),
+                                            self._stream()), self.handle)
+        return out
+
     # -- decode stages, separately callable ------------------------------------------
     def nms_device(self, heat, factor: float, thre1: float, mode: int = 0):
         """Peak search + refinement on ``heat [B,h,w,14]`` (CUDA float32).  Returns the device peak table

@@ -6,14 +6,16 @@ and return value ``(canvas, joint_list, person_to_joint_assoc, joints)``
 (``(0,)`` when empty), ``person_to_joint_assoc`` float64 ``(P, 16)`` (``(0,)`` when
 empty), ``joints`` float32 ``(P, 42)``.  The peak search, patch refinement, PAF
 line-integral scoring and grouping run in the CUDA decode chain (``lwop_decode``);
-only the canvas drawing of ``plot_pose`` stays on the host (cv2), as the survey's
-scope table allows.
+the canvas drawing of ``plot_pose`` runs on the host with cv2 by default, as the survey's
+scope table allows, or in the CUDA rasteriser (``lwop_draw_poses``: ``LWOP_DRAW=gpu`` /
+``plot_pose_device`` / ``Engine.draw_poses``), which paints the same bytes.
 
 ``decode_pose_batch`` is the batched form the GPU path is built for.
 """
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -79,11 +81,8 @@ def decode_pose_batch(img_hw, param, heatmaps, pafs, device: int = 0) -> List["e
     return e.decode(heat, paf, (H, W), float(param['thre1']), float(param['thre2']))
 
 
-def plot_pose(img_orig, joint_list, person_to_joint_assoc, bool_fast_plot=True):
-    """Keypoint table ``(P, 14, 3)`` float32 and the drawn canvas (reference :399-457)."""
-    import cv2
-    canvas = img_orig.copy()
-    persons = np.asarray(person_to_joint_assoc)
+def _keypoint_table(joint_list, persons) -> np.ndarray:
+    """``joints (P, 14, 3)`` of ``plot_pose`` (reference :403-429)."""
     n = persons.shape[0]
     joints = np.zeros((n, 14, 3), dtype=np.float32)
     for k in range(n):
@@ -92,9 +91,62 @@ def plot_pose(img_orig, joint_list, person_to_joint_assoc, bool_fast_plot=True):
             ids = row[[a, b]].astype(int)
             if -1 in ids:
                 continue
-            pts = joint_list[ids, 0:2]
-            for jid, pt in zip(ids, pts):
+            for jid, pt in zip(ids, joint_list[ids, 0:2]):
                 joints[k, int(joint_list[jid, -1]), :] = [pt[0], pt[1], 1]
+    return joints
+
+
+def plot_pose_device(img_orig, joint_list, person_to_joint_assoc, device: int = 0) -> np.ndarray:
+    """The canvas of ``plot_pose`` rasterised by the CUDA kernel (``lwop_draw_poses``): same circles and lines, byte
+    for byte, as cv2 draws them (reference :431-436).  Host arrays in, host canvas out; the batched, device-resident
+    form is :meth:`engine.Engine.draw_poses`."""
+    torch = _torch()
+    engine.require_gpu(device)
+    dev = torch.device("cuda", device)
+    img = np.ascontiguousarray(img_orig)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("img_orig must be uint8 [H, W, 3]")
+    persons = np.asarray(person_to_joint_assoc, dtype=np.float64)
+    persons = persons.reshape(-1, 16) if persons.size else np.zeros((0, 16))
+    jl = np.asarray(joint_list, dtype=np.float64)
+    jl = jl.reshape(-1, 6) if jl.size else np.zeros((0, 6))
+    if persons.shape[0] > _lib.MAX_PERSONS or jl.shape[0] > _lib.MAX_JOINTS:
+        raise _lib.LwopError(_lib.ERR_OVERFLOW, "more persons / joints than the device tables hold")
+    ids = persons[:, :14]
+    if ids.size and (ids.max() >= jl.shape[0] or ids.min() < -1):
+        raise IndexError("person table refers to a joint id outside joint_list")      # the reference's fancy index raises too
+    counts = np.zeros((1, _lib.COUNTS), dtype=np.int32)
+    counts[0, 0], counts[0, 1] = jl.shape[0], persons.shape[0]
+    tj = np.zeros((1, _lib.MAX_JOINTS, 6), dtype=np.float64)
+    tj[0, :jl.shape[0]] = jl
+    tp = np.zeros((1, _lib.MAX_PERSONS, 16), dtype=np.float64)
+    tp[0, :persons.shape[0]] = persons
+    tables = {"counts": torch.from_numpy(counts).to(dev), "joints": torch.from_numpy(tj).to(dev),
+              "persons": torch.from_numpy(tp).to(dev)}
+    e = _decode_engine(16, 16, 1, device)
+    canvas = e.draw_poses(torch.from_numpy(img).to(dev)[None], tables)
+    return canvas[0].cpu().numpy()
+
+
+def plot_pose(img_orig, joint_list, person_to_joint_assoc, bool_fast_plot=True):
+    """Keypoint table ``(P, 14, 3)`` float32 and the drawn canvas (reference :399-457).  The canvas is drawn on the
+    host with cv2, as the reference does, unless ``LWOP_DRAW=gpu`` selects the CUDA rasteriser
+    (:func:`plot_pose_device`; same bytes)."""
+    persons = np.asarray(person_to_joint_assoc)
+    if persons.size == 0:
+        persons = np.zeros((0, 16))
+    joints = _keypoint_table(joint_list, persons)
+    if os.environ.get("LWOP_DRAW", "") == "gpu":
+        return plot_pose_device(img_orig, joint_list, persons), joints
+    import cv2
+    canvas = img_orig.copy()
+    for k in range(persons.shape[0]):
+        row = persons[k]
+        for a, b in joint_to_limb_heatmap_relationship:
+            ids = row[[a, b]].astype(int)
+            if -1 in ids:
+                continue
+            pts = joint_list[ids, 0:2]
             for pt in pts:
                 cv2.circle(canvas, tuple(pt[0:2].astype(int)), 3, (255, 255, 255), thickness=-1)
             cv2.line(canvas, tuple(pts[0].astype(int)), tuple(pts[1].astype(int)),

@@ -71,6 +71,13 @@ def test_run_frames_matches_frame_by_frame_path():
         assert np.array_equal(one.person_to_joint_assoc, r.person_to_joint_assoc)
         assert np.array_equal(one.joints, r.joints)
         assert r.canvas().shape == (256, 256, 3)
+    # canvases rasterised on the device from the device-resident tables = the host cv2 drawing of the fetched tables
+    drawn = runner.run_frames(frames, keep_frames=True, draw=True)
+    for r in drawn:
+        assert r.canvas_data is not None and r.canvas() is r.canvas_data
+        host = r.img_data.copy() if not r.person_to_joint_assoc.size else \
+            pose_decode.plot_pose(r.img_data, r.joint_list, r.person_to_joint_assoc)[0]
+        assert np.array_equal(r.canvas_data, host)
 
 
 def test_keypoint_annotations_json_shape(tmp_path):
