@@ -12,7 +12,9 @@ import re
 from typing import Dict, List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lwop.so")
+# LWOP_LIB_PATH: development A/B of differently compiled builds of the same library (tools/ab_variant.sh); same loud
+# failure if the file is missing or lacks a symbol
+LIB_PATH = os.environ.get("LWOP_LIB_PATH") or os.path.join(_HERE, "_lwop.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lwop.h")
 
 # constants mirrored from include/lwop.h
