@@ -107,14 +107,19 @@ class ClockSampler:
             self.stop_flag = True
             self.thread.join(timeout=1)
             n = self.nvml
-            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            # every bit of NVML's clocks-event-reasons mask seen under load is named (gpu_idle aside: it is what an idle
+            # sample between two steps reports), so that clocks below the maximum never come without their reason
+            names = {"applications_clocks_setting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8, "sync_boost": 0x10,
+                     "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80,
+                     "display_clock_setting": 0x100}
             reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
             sm = [m for m, _ in self.samples]
             return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                    "samples": len(sm), "source": "nvml"}
+                    "samples": len(sm), "source": "nvml", "reasons_mask_or": hex(mask),
+                    "sm_mhz_min_max": [min(sm), max(sm)] if sm else None}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

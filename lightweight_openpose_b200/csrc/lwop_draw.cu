@@ -228,28 +228,29 @@ __device__ __forceinline__ void disc3(const Plot &plot, long long cx, long long 
     }
 }
 
-constexpr int kDrawWarps = 13;   // one warp per limb type; CTA = one person of one image
+constexpr int kDrawWarps = 13;        // one warp per limb type
+constexpr int kDrawPersonSlots = 8;   // CTAs per image; CTA s takes persons s, s + 8, ... (the person count is only known on the device)
 
 __global__ void __launch_bounds__(32 * kDrawWarps)
 draw_mark_kernel(const int *__restrict__ counts, const double *__restrict__ joints, const double *__restrict__ persons,
                  int *__restrict__ prio, int H, int W) {
-    const int b = blockIdx.y, person = blockIdx.x;
+    const int b = blockIdx.y;
     const int n_persons = min(counts[(size_t)b * LWOP_COUNTS + 1], LWOP_MAX_PERSONS);
-    if (person >= n_persons) return;
     const int limb = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double *row = persons + ((size_t)b * LWOP_MAX_PERSONS + person) * 16;
-    // person_joint_info[joint_to_limb_heatmap_relationship[limb_type]].astype(int); -1 = joint not set (:409-415)
-    const int ia = (int)row[c_limb[limb][0]], ib = (int)row[c_limb[limb][1]];
-    if (ia == -1 || ib == -1) return;
-    if (ia < 0 || ib < 0 || ia >= LWOP_MAX_JOINTS || ib >= LWOP_MAX_JOINTS) return;   // not a row of this table
-    const double *ja = joints + ((size_t)b * LWOP_MAX_JOINTS + ia) * 6, *jb = joints + ((size_t)b * LWOP_MAX_JOINTS + ib) * 6;
-    const long long xa = (long long)ja[0], ya = (long long)ja[1];      // joint[0:2].astype(int): truncation
-    const long long xb = (long long)jb[0], yb = (long long)jb[1];
-    Plot plot{prio + (size_t)b * H * W, W, H, 2 * (person * LWOP_NUM_LIMBS + limb)};
-    disc3(plot, xa, ya, lane);
-    disc3(plot, xb, yb, lane);
-    plot.value += 1;
-    thick_line2(plot, xa, ya, xb, yb, lane);
+    for (int person = blockIdx.x; person < n_persons; person += gridDim.x) {
+        const double *row = persons + ((size_t)b * LWOP_MAX_PERSONS + person) * 16;
+        // person_joint_info[joint_to_limb_heatmap_relationship[limb_type]].astype(int); -1 = joint not set (:409-415)
+        const int ia = (int)row[c_limb[limb][0]], ib = (int)row[c_limb[limb][1]];
+        if (ia < 0 || ib < 0 || ia >= LWOP_MAX_JOINTS || ib >= LWOP_MAX_JOINTS) continue;   // not set / not a row of this table
+        const double *ja = joints + ((size_t)b * LWOP_MAX_JOINTS + ia) * 6, *jb = joints + ((size_t)b * LWOP_MAX_JOINTS + ib) * 6;
+        const long long xa = (long long)ja[0], ya = (long long)ja[1];      // joint[0:2].astype(int): truncation
+        const long long xb = (long long)jb[0], yb = (long long)jb[1];
+        Plot plot{prio + (size_t)b * H * W, W, H, 2 * (person * LWOP_NUM_LIMBS + limb)};
+        disc3(plot, xa, ya, lane);
+        disc3(plot, xb, yb, lane);
+        plot.value += 1;
+        thick_line2(plot, xa, ya, xb, yb, lane);
+    }
 }
 
 __device__ __forceinline__ void resolve_pixel(int p, unsigned char &c0, unsigned char &c1, unsigned char &c2) {
@@ -306,7 +307,7 @@ draw_resolve1_kernel(const unsigned char *img, int *__restrict__ prio, unsigned 
 
 cudaError_t launch_draw_poses(const uint8_t *img, int B, int H, int W, const int *counts, const double *joints,
                               const double *persons, int *prio, uint8_t *canvas, cudaStream_t s, long long *launches) {
-    draw_mark_kernel<<<dim3(LWOP_MAX_PERSONS, B), 32 * kDrawWarps, 0, s>>>(counts, joints, persons, prio, H, W);
+    draw_mark_kernel<<<dim3(kDrawPersonSlots, B), 32 * kDrawWarps, 0, s>>>(counts, joints, persons, prio, H, W);
     ++*launches;
     const size_t n = (size_t)B * H * W;
     const bool aligned = (((uintptr_t)img | (uintptr_t)canvas) & 3) == 0;
