@@ -628,13 +628,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         while pending:
             finish(pending.pop(0))
 
-    def time_e2e(bufs):
+    def time_e2e(bufs, sampler=None):
         # warm-up: every engine must have seen each of its (upload slot, result lane) pairs once -- each new pair captures
         # a CUDA graph (eager pass + synchronisation), which must not happen inside the timed region
         run_e2e(bufs, 2 * pool.capacity + 2)
         barrier()
         for k in host_s:
             host_s[k] = 0.0
+        if sampler is not None:
+            sampler.start()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -645,7 +647,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         barrier()
         return max(e0.elapsed_time(e1), wall), wall
 
-    e2e_ms, e2e_wall_ms = time_e2e(u8_host)
+    # the e2e region runs after ~0.3 s of load, usually at the power-capped clock, while the short `value` region before it
+    # may still have boosted: its clocks are sampled separately (timed part only)
+    sampler_e2e = ClockSampler(local_rank)
+    e2e_ms, e2e_wall_ms = time_e2e(u8_host, sampler_e2e)
+    clocks_e2e = sampler_e2e.stop()
     if os.environ.get("BENCH_TRACE") and rank == 0:
         print("host ms per step:", {k: round(1e3 * v / args.steps, 4) for k, v in host_s.items()},
               "wall ms per step:", round(e2e_wall_ms / args.steps, 4), file=sys.stderr)
@@ -725,6 +731,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                         "h2d_bytes_per_step": G * H * W * 3 * 4} if args.e2e_f32 else None),
                 "e2e_one_synchronous_call_per_step": {"value": total_images / (e2e_sync_ms * 1e-3), "unit": "images/s"},
                 "e2e_wall_ms_per_step": e2e_wall_ms / args.steps,
+                "e2e_clocks": clocks_e2e,
                 **extras,
             },
             "roofline": roof,

@@ -233,7 +233,9 @@ int lwop_infer_host_begin(lwop_handle *h, const void *images_host, int is_u8, in
 int lwop_infer_host_end(lwop_handle *h, int ticket);
 
 /* Tunables: "chunk" = images per pipeline stage of lwop_infer_host (0 = default: 64 for float32 frames, 128 for
- * uint8; the asynchronous entry submits the whole batch as one chunk). */
+ * uint8; the asynchronous entry submits the whole batch as one chunk).  "copy_stream" = a caller-owned cudaStream_t
+ * (passed as an integer) that carries this handle's uploads instead of its private copy stream: handles of one device
+ * that share it upload in submission order, each batch at the full PCIe rate (0 = private stream again). */
 int lwop_set_option(lwop_handle *h, const char *name, long long value);
 
 /* ---- per-op entries mirroring src/net_factory.py (unit tests, eager mode) ---- */

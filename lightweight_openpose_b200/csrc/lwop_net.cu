@@ -152,6 +152,7 @@ struct lwop_handle {
     float *slot_heat[2] = {}, *slot_paf[2] = {};
     cudaEvent_t ev_h2d[2] = {}, ev_fwd[2] = {}, ev_done[2] = {}, ev_start = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr, decode_stream = nullptr;
+    bool copy_stream_borrowed = false;           // set through the "copy_stream" option: several handles share one upload queue
     lwop_decode_tables own_tables = {};
     int own_tables_batch = 0;
     // batches in flight through lwop_infer_host_begin / _end: each lane owns its decode tables and packed buffers
@@ -783,7 +784,7 @@ int lwop_destroy(lwop_handle *h) {
     }
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->copy_stream && !h->copy_stream_borrowed) cudaStreamDestroy(h->copy_stream);
     if (h->decode_stream) cudaStreamDestroy(h->decode_stream);
     for (auto &ln : h->lanes) {
         if (ln.tables.counts) cudaFree(ln.tables.counts);
@@ -1229,6 +1230,19 @@ int lwop_set_option(lwop_handle *h, const char *name, long long value) {
     if (strcmp(name, "chunk") == 0) {
         if (value < 0) return fail(h, LWOP_ERR_INVALID, "chunk must be >= 0 (0 = library default)");
         h->chunk = (int)value;
+        return LWOP_OK;
+    }
+    if (strcmp(name, "copy_stream") == 0) {
+        // uploads of lwop_infer_host* go through this caller-owned stream (a cudaStream_t passed as an integer) instead of
+        // the handle's private one: handles that share it upload in submission order, one batch at a time at full PCIe
+        // rate, instead of all at once at a fraction of it each (0 = back to a private stream)
+        if (h->copy_stream && !h->copy_stream_borrowed) {
+            cudaSetDevice(h->device);
+            cudaStreamSynchronize(h->copy_stream);
+            cudaStreamDestroy(h->copy_stream);
+        }
+        h->copy_stream = (cudaStream_t)(uintptr_t)value;
+        h->copy_stream_borrowed = value != 0;
         return LWOP_OK;
     }
     return fail(h, LWOP_ERR_INVALID, std::string("unknown option ") + name);

@@ -9,6 +9,7 @@ build graph -> ``Saver.restore`` -> per frame ``sess.run([cpm, paf])`` -> ``deco
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -548,6 +549,13 @@ class EnginePool:
         self.capacity = lanes * depth
         self.engines = [Engine(height, width, max_batch=max_batch, device=device,
                                stream=torch.cuda.Stream(device=device)) for _ in range(lanes)]
+        # one upload queue for the pool: with a private copy stream per engine the uploads of every batch in flight run
+        # concurrently and share PCIe, so the FIRST batch lands only when nearly all have (a long pipeline fill);
+        # through one stream they land in submission order, each at the full rate
+        self._copy_stream = torch.cuda.Stream(device=device)
+        if os.environ.get("LWOP_POOL_SHARED_COPY", "1") != "0":
+            for e in self.engines:
+                e.set_option("copy_stream", self._copy_stream.cuda_stream)
         self._next = 0
         self._pending: List[Tuple[int, int]] = []          # (lane, ticket) in submission order
         self._events = [torch.cuda.Event() for _ in range(lanes)]

@@ -1,9 +1,9 @@
-for B in 32 128; do
-for S in 20 200; do
-echo "== batch $B steps $S"
-BENCH_TRACE=1 LWOP_TRACE_HOST=1 python bench.py --batch $B --steps $S --warmup 5 --no-cpu --no-extras 2> gpurun_out/e2e_probe_${B}_${S}.err | python -c "
+#!/bin/bash
+# e2e (host-buffer path) against value (device-resident) at small slices on ONE GPU, 20 and 200 steps, with the pool's
+# uploads through one shared copy stream (default) and through a private stream per engine (LWOP_POOL_SHARED_COPY=0)
+for SH in 1 0; do for B in 32 128; do for S in 20 200; do
+LWOP_POOL_SHARED_COPY=$SH python bench.py --batch $B --steps $S --warmup 5 --no-cpu --no-extras 2> /dev/null | python -c "
 import json,sys
 b=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=b['config']
-print('value',round(b['value']),'e2e',round(b['e2e']['value']),'ratio',round(b['e2e']['value']/b['value'],3),'ms/step',round(b['ms_per_step'],4),'e2e wall ms/step',round(c['e2e_wall_ms_per_step'],4),'lanes',c['steps_in_flight_per_gpu'],c['e2e_steps_in_flight_per_gpu'],'clk',b['clocks']['sm_mhz'], 'sync',round(c['e2e_one_synchronous_call_per_step']['value']))"
-grep -E "host ms per step|lwop host trace" gpurun_out/e2e_probe_${B}_${S}.err | tail -3
-done; done
+print('shared_copy $SH batch $B steps $S value',round(b['value']),'e2e',round(b['e2e']['value']),'ratio',round(b['e2e']['value']/b['value'],3),'ms/step',round(b['ms_per_step'],4),'e2e wall ms/step',round(c['e2e_wall_ms_per_step'],4),'clk',b['clocks']['sm_mhz'])"
+done; done; done
