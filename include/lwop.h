@@ -262,6 +262,13 @@ int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype,
                       int batch, int height, int width, int channels,
                       const float *w_dev, int stride, int dilation, void *out_dev, void *stream);
 
+/* The same for any kernel_size (conv_dw / conv_dw_no_bn take it as an argument, net_factory.py:14,23, although the
+ * network only uses 3): w_dev float32 [ksize*ksize][C]; 'same' padding as TensorFlow splits it (smaller half first).
+ * ksize == 3 is lwop_depthwise3x3; other sizes run a generic CUDA-core kernel (fp32 accumulation) in every mode. */
+int lwop_depthwise2d(lwop_handle *h, int mode, const void *in_dev, int dtype,
+                     int batch, int height, int width, int channels,
+                     const float *w_dev, int ksize, int stride, int dilation, void *out_dev, void *stream);
+
 /* conv_dw() / conv_dw_no_bn(): tf.layers.separable_conv2d (depthwise 3x3 then pointwise 1x1, nothing in
  * between) + folded batch norm / bias + activation (net_factory.py:15-19,25-29), optional residual added after
  * the activation (lightweight_openpose.py:27).  LWOP_MODE_BF16: ONE fused kernel (CUDA-core depthwise feeding

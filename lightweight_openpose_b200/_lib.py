@@ -76,6 +76,7 @@ SIGNATURES: Dict[str, tuple] = {
     "lwop_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "lwop_first_conv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lwop_depthwise3x3": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "lwop_depthwise2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "lwop_separable_conv2d": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lwop_head_pair": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lwop_same_out": (_i, [_i, _i]),

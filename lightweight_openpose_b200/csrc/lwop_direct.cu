@@ -120,7 +120,7 @@ cudaError_t launch_conv_direct(const ConvArgs &a, cudaStream_t s) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 depthwise_simple_kernel(const T *__restrict__ in, const float *__restrict__ w, T *__restrict__ out, int B, int H,
-                        int W, int C, int Ho, int Wo, int stride, int dil, int pad_t, int pad_l) {
+                        int W, int C, int Ho, int Wo, int ksize, int stride, int dil, int pad_t, int pad_l) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * Ho * Wo * C;
     if (idx >= total) return;
@@ -131,32 +131,30 @@ depthwise_simple_kernel(const T *__restrict__ in, const float *__restrict__ w, T
     int oy = (int)(p % Ho);
     int b = (int)(p / Ho);
     float acc = 0.0f;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
+    for (int dy = 0; dy < ksize; ++dy) {
         int iy = oy * stride - pad_t + dy * dil;
         if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int dx = 0; dx < ksize; ++dx) {
             int ix = ox * stride - pad_l + dx * dil;
             if (ix < 0 || ix >= W) continue;
-            acc = fmaf(ld_as_float(in + (((long long)b * H + iy) * W + ix) * C + c), w[(dy * 3 + dx) * C + c], acc);
+            acc = fmaf(ld_as_float(in + (((long long)b * H + iy) * W + ix) * C + c), w[(dy * ksize + dx) * C + c], acc);
         }
     }
     st_from_float(out + idx, acc);
 }
 
 cudaError_t launch_depthwise_simple(const DwArgs &a, cudaStream_t s) {
-    SamePad ph = same_pad(a.H, 3, a.stride, a.dil), pw = same_pad(a.W, 3, a.stride, a.dil);
+    SamePad ph = same_pad(a.H, a.ksize, a.stride, a.dil), pw = same_pad(a.W, a.ksize, a.stride, a.dil);
     long long total = (long long)a.B * ph.out * pw.out * a.C;
     unsigned grid = (unsigned)((total + 255) / 256);
     if (a.dtype == LWOP_DT_F32)
         depthwise_simple_kernel<float><<<grid, 256, 0, s>>>((const float *)a.in, a.w, (float *)a.out, a.B, a.H, a.W,
-                                                            a.C, ph.out, pw.out, a.stride, a.dil, ph.before,
-                                                            pw.before);
+                                                            a.C, ph.out, pw.out, a.ksize, a.stride, a.dil,
+                                                            ph.before, pw.before);
     else
         depthwise_simple_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
-            (const __nv_bfloat16 *)a.in, a.w, (__nv_bfloat16 *)a.out, a.B, a.H, a.W, a.C, ph.out, pw.out, a.stride,
-            a.dil, ph.before, pw.before);
+            (const __nv_bfloat16 *)a.in, a.w, (__nv_bfloat16 *)a.out, a.B, a.H, a.W, a.C, ph.out, pw.out, a.ksize,
+            a.stride, a.dil, ph.before, pw.before);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ struct DwArgs {
     int dtype;
     const float *w;        // [9][C] fp32
     int B, H, W, C, stride, dil;
+    int ksize = 3;         // depthwise kernel edge (the tcgen05-side / vector kernels are 3x3 only; others take the generic kernel)
 };
 
 // lwop_direct.cu

@@ -1340,6 +1340,23 @@ int lwop_depthwise3x3(lwop_handle *h, int mode, const void *in_dev, int dtype, i
     return LWOP_OK;
 }
 
+int lwop_depthwise2d(lwop_handle *h, int mode, const void *in_dev, int dtype, int batch, int height, int width,
+                     int channels, const float *w_dev, int ksize, int stride, int dilation, void *out_dev, void *stream) {
+    if (ksize == 3)
+        return lwop_depthwise3x3(h, mode, in_dev, dtype, batch, height, width, channels, w_dev, stride, dilation, out_dev, stream);
+    if (!h || !in_dev || !w_dev || !out_dev) return fail(h, LWOP_ERR_INVALID, "null argument");
+    if (ksize < 1 || ksize > 15 || stride < 1 || dilation < 1 || batch < 1 || height < 1 || width < 1 || channels < 1)
+        return fail(h, LWOP_ERR_INVALID, "bad depthwise geometry");
+    if (dtype != LWOP_DT_F32 && dtype != LWOP_DT_BF16) return fail(h, LWOP_ERR_INVALID, "bad dtype");
+    CU_OK(h, cudaSetDevice(h->device));
+    DwArgs a{};
+    a.in = in_dev; a.out = out_dev; a.dtype = dtype; a.w = w_dev;
+    a.B = batch; a.H = height; a.W = width; a.C = channels; a.stride = stride; a.dil = dilation; a.ksize = ksize;
+    CU_OK(h, launch_depthwise_simple(a, (cudaStream_t)stream));      // fp32 accumulation on CUDA cores, any mode
+    h->launches++;
+    return LWOP_OK;
+}
+
 int lwop_separable_conv2d(lwop_handle *h, int mode, const void *in_dev, int batch, int height, int width, int cin,
                           const float *dw_w_dev, const float *pw_w_dev, const float *bias_dev, int cout,
                           int dilation, int act, const void *residual_dev, void *out_dev, void *stream) {

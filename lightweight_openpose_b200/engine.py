@@ -644,8 +644,15 @@ def set_variables(variables: Dict[str, np.ndarray], source: str = "variables") -
     global _variables, _variables_source
     _variables, _variables_source = variables, source
     with _engines_lock:
-        for e in _engines.values():
-            e.load_variables(variables, source)
+        if graph.fits_executor(variables):
+            for e in _engines.values():
+                e.load_variables(variables, source)
+        else:
+            # head widths other than the executor's 14 / 26: only the op-level (eager) graph can run these variables;
+            # the cached whole-network engines would keep the previous weights, so they go
+            for e in _engines.values():
+                e.close()
+            _engines.clear()
 
 
 def load_weights(prefix: Optional[str] = None, seed: int = 61236) -> str:

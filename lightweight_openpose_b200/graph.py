@@ -43,6 +43,7 @@ class Layer:
     act: int
     bias: bool
     note: str = ""
+    dw_k: int = 3          # kernel size of the depthwise half of a separable layer (the network only uses 3)
 
 
 class _Scope:
@@ -140,8 +141,8 @@ class FoldedLayer:
 def fold_layer(layer: Layer, v: Dict[str, np.ndarray]) -> FoldedLayer:
     if layer.kind == KIND_SEPARABLE:
         dwk = np.asarray(v[layer.name + "/depthwise_kernel"], dtype=np.float64)   # [3,3,cin,1]
-        assert dwk.shape == (3, 3, layer.cin, 1), (layer.name, dwk.shape)
-        dw = dwk.reshape(9, layer.cin)
+        assert dwk.shape == (layer.dw_k, layer.dw_k, layer.cin, 1), (layer.name, dwk.shape)
+        dw = dwk.reshape(layer.dw_k * layer.dw_k, layer.cin)
         w = np.asarray(v[layer.name + "/pointwise_kernel"], dtype=np.float64)     # [1,1,cin,cout]
     else:
         dw = None
@@ -161,6 +162,17 @@ def fold_layer(layer: Layer, v: Dict[str, np.ndarray]) -> FoldedLayer:
     w = np.ascontiguousarray(w.reshape(layer.k * layer.k, layer.cin, layer.cout).transpose(2, 0, 1))
     return FoldedLayer(None if dw is None else dw.astype(np.float32),
                        w.astype(np.float32), b.astype(np.float32))
+
+
+def fits_executor(v: Dict[str, np.ndarray]) -> bool:
+    """Whether a variable set has the shapes of the layer table the whole-network executor is built for (the shipped
+    checkpoint: 14 keypoint and 26 PAF channels).  Other head widths run through the op-level graph only."""
+    for layer in LAYERS:
+        key = layer.name + ("/pointwise_kernel" if layer.kind == KIND_SEPARABLE else "/kernel")
+        w = v.get(key)
+        if w is None or tuple(np.shape(w))[2:] != (layer.cin, layer.cout):
+            return False
+    return True
 
 
 def fold_all(v: Dict[str, np.ndarray], layers: Optional[List[Layer]] = None) -> List[FoldedLayer]:

@@ -11,7 +11,8 @@ tensor input, numpy arrays for numpy input (what ``sess.run`` hands back).
 Default path: the whole-network executor behind ``lwop_forward`` (one CUDA graph
 of hand-written sm_100a kernels).  ``eager=True`` instead composes the network
 from the ``net_factory`` ops exactly as the reference source does, which is the
-layer-by-layer restatement the parity tests compare against the executor.
+layer-by-layer restatement the parity tests compare against the executor -- and
+what runs when ``num_joints`` / ``num_pafs`` differ from the checkpoint's 14 / 26.
 
 Weights are bound once with :func:`load_weights` (replaces
 ``tf.train.Saver().restore``); without a call the default checkpoint
@@ -93,8 +94,10 @@ def lightweight_openpose(inputs, num_joints, num_pafs, is_training=True, *, retu
             "is_training=True: only the inference hot path is implemented (the reference's callers on this "
             "path pass is_training=False, test&eval/model_test.py:42)")
     if num_joints != 14 or num_pafs != 26:
-        raise NotImplementedError("the shipped checkpoint has 14 keypoint and 26 PAF channels "
-                                  "(reference src/train_config.py:25-26)")
+        # the whole-network executor (and the decode chain) are built for the shipped checkpoint's 14 keypoint / 26 PAF
+        # channels (reference src/train_config.py:25-26); any other head width runs the same graph composed from the
+        # net_factory ops, against whatever variables of matching shapes the caller has bound
+        eager = True
     torch = _torch()
     was_numpy = isinstance(inputs, np.ndarray)
     dev_index = device if device is not None else (0 if was_numpy or inputs.device.type != "cuda"

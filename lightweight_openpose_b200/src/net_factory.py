@@ -123,12 +123,13 @@ def conv(inputs, out_channels, kernel_size=3, bn=True, dilation=1, stride=1, rel
                       _lib.ACT_RELU if relu else _lib.ACT_NONE, out_dtype)
 
 
-def _separable(inputs, out_channels, stride, dilation, bn, act):
+def _separable(inputs, out_channels, stride, dilation, bn, act, kernel_size=3):
     torch = _torch()
     vname = _scope.next_name("separable_conv2d")
     bn_name = _scope.next_name("batch_normalization") if bn else None
     cin = inputs.shape[-1]
-    layer = graph.Layer(-1, graph.KIND_SEPARABLE, vname, bn_name, cin, out_channels, 1, stride, dilation, act, False)
+    layer = graph.Layer(-1, graph.KIND_SEPARABLE, vname, bn_name, cin, out_channels, 1, stride, dilation, act, False,
+                        dw_k=int(kernel_size))
     wts = _device_weights(vname, layer, inputs.device)
     x = inputs.contiguous()
     if x.dtype == torch.float32 and _mode != "fp32":
@@ -139,26 +140,23 @@ def _separable(inputs, out_channels, stride, dilation, bn, act):
     e = _handle(x.device.index or 0)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     vec_ok = x.dtype == torch.bfloat16 and cin % 8 == 0 and _mode == "bf16"
-    _lib.check(e.lib.lwop_depthwise3x3(e.handle, _lib.MODE_BF16 if vec_ok else _lib.MODE_FP32_CHECK, x.data_ptr(),
-                                       _dt(x), B, H, W, cin, wts["dw"].data_ptr(), stride, dilation,
-                                       mid.data_ptr(), stream), e.handle)
+    _lib.check(e.lib.lwop_depthwise2d(e.handle, _lib.MODE_BF16 if vec_ok else _lib.MODE_FP32_CHECK, x.data_ptr(),
+                                      _dt(x), B, H, W, cin, wts["dw"].data_ptr(), int(kernel_size), stride, dilation,
+                                      mid.data_ptr(), stream), e.handle)
     return _conv_call(mid, wts, out_channels, 1, 1, 1, act, _act_dtype())
 
 
 def conv_dw(inputs, out_channels, kernel_size=3, stride=1, dilation=1, training=True, name=''):
-    """separable conv (depthwise 3x3 -> pointwise 1x1, no bias) + batch norm + ReLU -- net_factory.py:14-21."""
+    """separable conv (depthwise ``kernel_size`` -> pointwise 1x1, no bias) + batch norm + ReLU -- net_factory.py:14-21.
+    3x3 (what the network uses) runs the TMA / vector depthwise kernels, other sizes a generic CUDA-core kernel."""
     if training:
         _training_error()
-    if kernel_size != 3:
-        raise NotImplementedError("depthwise kernels other than 3x3")
-    return _separable(inputs, out_channels, stride, dilation, True, _lib.ACT_RELU)
+    return _separable(inputs, out_channels, stride, dilation, True, _lib.ACT_RELU, kernel_size)
 
 
 def conv_dw_no_bn(inputs, out_channels, kernel_size=3, stride=1, dilation=1, training=True, name=''):
     """separable conv + ELU (no batch norm, so ``training`` is irrelevant) -- net_factory.py:23-31."""
-    if kernel_size != 3:
-        raise NotImplementedError("depthwise kernels other than 3x3")
-    return _separable(inputs, out_channels, stride, dilation, False, _lib.ACT_ELU)
+    return _separable(inputs, out_channels, stride, dilation, False, _lib.ACT_ELU, kernel_size)
 
 
 def add(a, b):

@@ -204,3 +204,33 @@ def test_forward_on_rough_random_weights():
         assert er > 1e-4 * std                      # the emulation does perturb: the comparison is not vacuous
         assert gr <= 1.25 * er and gm <= 1.5 * em, (k, gm, gr, em, er)
         assert gr <= 0.02 * std, (k, gr, std)
+
+
+def test_other_head_widths_run_the_eager_graph(variables):
+    """lightweight_openpose(inputs, num_joints, num_pafs) with widths other than the checkpoint's 14 / 26 (reference
+    signature, src/lightweight_openpose.py:8): same graph from the net_factory ops on a variable set of matching shapes."""
+    from lightweight_openpose_b200 import graph
+    nj, npaf = 19, 38
+    rng = np.random.default_rng(3)
+    v = dict(variables)
+    for layer in graph.LAYERS:
+        if layer.note in ("heatmaps1", "heatmaps2", "pafs1", "pafs2"):
+            width = nj if layer.note.startswith("heat") else npaf
+            k = v[layer.name + "/kernel"]
+            v[layer.name + "/kernel"] = (rng.standard_normal(k.shape[:3] + (width,)) * k.std()).astype(np.float32)
+            v[layer.name + "/bias"] = rng.normal(0, 0.01, width).astype(np.float32)
+        elif layer.kind == graph.KIND_CONV and layer.cin == 40:
+            k = v[layer.name + "/kernel"]
+            v[layer.name + "/kernel"] = (rng.standard_normal((1, 1, nj + npaf, k.shape[3])) * k.std()).astype(np.float32)
+    x = synth.synth_batch([5], 128, 128)
+    oh, op = ForwardOracle(v)(x, num_joints=nj, num_pafs=npaf)
+    assert oh.shape == (1, 16, 16, nj) and op.shape == (1, 16, 16, npaf)
+    engine.set_variables(v, "other widths")
+    try:
+        h, p = lightweight_openpose(x, nj, npaf, is_training=False, mode="fp32")
+        assert h.shape == oh.shape and p.shape == op.shape
+        assert _maxabs(h, oh) <= TOL_FP32 and _maxabs(p, op) <= TOL_FP32
+        hb, pb = lightweight_openpose(x, nj, npaf, is_training=False, mode="bf16")
+        assert _maxabs(hb, oh) <= 2 * TOL_BF16 and _maxabs(pb, op) <= 2 * TOL_BF16
+    finally:
+        engine.set_variables(variables, "synthetic")

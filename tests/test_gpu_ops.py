@@ -294,3 +294,64 @@ def test_fused_separable_with_residual_is_bitwise_repeatable(eng):
             ref = out
         else:
             assert torch.equal(out, ref), f"launch {run} differs from launch 0 in {int((out != ref).sum())} elements"
+
+
+@pytest.mark.parametrize("ksize,stride,dil,cin,cout", [(5, 1, 1, 32, 48), (5, 2, 1, 24, 64), (1, 1, 1, 64, 32), (7, 1, 2, 16, 16),
+                                                        (2, 2, 1, 32, 32)])
+def test_conv_dw_with_other_kernel_sizes(ksize, stride, dil, cin, cout):
+    """conv_dw / conv_dw_no_bn take kernel_size (reference net_factory.py:14,23); the network only uses 3, other sizes run the
+    generic depthwise kernel + the 1x1 GEMM.  Against an fp64 torch-CPU separable conv with TensorFlow's 'same' padding."""
+    import torch.nn.functional as F
+    from lightweight_openpose_b200 import engine as eng_mod
+    from lightweight_openpose_b200.src import _scope, net_factory
+    from util import same_pad
+    rng = np.random.default_rng(ksize * 100 + stride * 10 + dil)
+    B, H, W = 2, 23, 30
+    x = rng.standard_normal((B, H, W, cin)).astype(np.float32)
+    v = {"T/separable_conv2d/depthwise_kernel": rng.standard_normal((ksize, ksize, cin, 1)).astype(np.float32) / ksize,
+         "T/separable_conv2d/pointwise_kernel": (rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)).astype(np.float32),
+         "T/batch_normalization/gamma": rng.uniform(0.5, 1.5, cout).astype(np.float32),
+         "T/batch_normalization/beta": rng.normal(0, 0.1, cout).astype(np.float32),
+         "T/batch_normalization/moving_mean": rng.normal(0, 0.1, cout).astype(np.float32),
+         "T/batch_normalization/moving_variance": rng.uniform(0.5, 1.5, cout).astype(np.float32)}
+    # conv_dw_no_bn gets a scope of its own: a variable name belongs to ONE layer (the folded weights are cached by name)
+    v["U/separable_conv2d/depthwise_kernel"] = v["T/separable_conv2d/depthwise_kernel"]
+    v["U/separable_conv2d/pointwise_kernel"] = v["T/separable_conv2d/pointwise_kernel"]
+
+    def reference(bn):
+        xt = torch.from_numpy(x).double().permute(0, 3, 1, 2)
+        _, pt, pb = same_pad(H, ksize, stride, dil)
+        _, pl, pr = same_pad(W, ksize, stride, dil)
+        xt = F.pad(xt, (pl, pr, pt, pb))
+        dw = torch.from_numpy(v["T/separable_conv2d/depthwise_kernel"]).double().permute(2, 3, 0, 1)        # [C,1,k,k]
+        y = F.conv2d(xt, dw, None, stride=stride, dilation=dil, groups=cin)
+        pw = torch.from_numpy(v["T/separable_conv2d/pointwise_kernel"]).double().permute(3, 2, 0, 1)
+        y = F.conv2d(y, pw)
+        if bn:
+            g, b_, m, var = (torch.from_numpy(v["T/batch_normalization/" + k]).double().view(1, -1, 1, 1)
+                             for k in ("gamma", "beta", "moving_mean", "moving_variance"))
+            y = torch.relu(g * (y - m) / torch.sqrt(var + 1e-3) + b_)
+        else:
+            y = F.elu(y)
+        return y.permute(0, 2, 3, 1).numpy()
+
+    saved = eng_mod.get_variables() if getattr(eng_mod, "_variables", None) is not None else None
+    eng_mod.set_variables(v, "test")
+    try:
+        xd = torch.from_numpy(x).cuda()
+        for mode, tol in (("fp32", 2e-5), ("bf16", 6e-2)):
+            net_factory.set_mode(mode)
+            for bn in (True, False):
+                _scope.reset()
+                with _scope.variable_scope("T" if bn else "U"):
+                    y = (net_factory.conv_dw(xd, cout, kernel_size=ksize, stride=stride, dilation=dil, training=False) if bn
+                         else net_factory.conv_dw_no_bn(xd, cout, kernel_size=ksize, stride=stride, dilation=dil))
+                want = reference(bn)
+                got = y.float().cpu().numpy()
+                assert got.shape == want.shape, (got.shape, want.shape)
+                scale = max(1.0, float(np.abs(want).max()))
+                assert float(np.abs(got - want).max()) <= tol * scale, (mode, bn, float(np.abs(got - want).max()), scale)
+    finally:
+        net_factory.set_mode("bf16")
+        if saved is not None:
+            eng_mod.set_variables(saved, "restored")
