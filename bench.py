@@ -48,7 +48,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_s: float = 0.002):
+        self.period = period_s
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
@@ -96,7 +97,7 @@ class ClockSampler:
                 self.samples.append((mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -649,7 +650,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     # the e2e region runs after ~0.3 s of load, usually at the power-capped clock, while the short `value` region before it
     # may still have boosted: its clocks are sampled separately (timed part only)
-    sampler_e2e = ClockSampler(local_rank)
+    sampler_e2e = ClockSampler(local_rank, period_s=0.01)
     e2e_ms, e2e_wall_ms = time_e2e(u8_host, sampler_e2e)
     clocks_e2e = sampler_e2e.stop()
     if os.environ.get("BENCH_TRACE") and rank == 0:
