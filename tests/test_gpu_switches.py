@@ -56,3 +56,38 @@ def test_every_kernel_selection_switch_gives_the_same_maps(tmp_path):
         # 2e-2 the bf16 path has against the oracle (BASELINE.json)
         assert d <= 2e-2, (sw, d)
     print(worst)
+
+
+POOL_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from lightweight_openpose_b200 import checkpoint, engine, synth
+v, src = checkpoint.load_or_synthesize()
+pool = engine.EnginePool(368, 368, max_batch=4, lanes=3, depth=2)
+pool.load_variables(v, src)
+batches = [torch.from_numpy(np.stack([synth.synth_image(10 * k + s, 368, 368) for s in range(4)])).pin_memory() for k in range(7)]
+out = {}
+for k, res in enumerate(pool.map(batches)):
+    out["counts%%d" %% k] = res.counts.copy()
+    out["joints%%d" %% k] = np.concatenate([r.joint_list.reshape(-1, 6) for r in res])
+    out["persons%%d" %% k] = np.concatenate([r.person_to_joint_assoc.reshape(-1, 16) for r in res])
+pool.close()
+np.savez(sys.argv[1], **out)
+""" % ROOT
+
+
+def test_pool_upload_stream_switch_gives_the_same_tables(tmp_path):
+    """LWOP_POOL_SHARED_COPY=0 (a private upload stream per engine instead of the pool's shared one): seven batches through
+    a 3-lane, depth-2 pool (the ring wraps, slots are reused) must give bit-identical result tables."""
+    outs = []
+    for i, sw in enumerate(({}, {"LWOP_POOL_SHARED_COPY": "0"})):
+        env = dict(os.environ)
+        env.update(sw)
+        path = str(tmp_path / f"pool{i}.npz")
+        r = subprocess.run([sys.executable, "-c", POOL_SCRIPT, path], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (sw, r.stderr[-2000:])
+        outs.append(dict(np.load(path)))
+    assert outs[0].keys() == outs[1].keys() and len(outs[0]) == 21
+    assert sum(int(outs[0][f"counts{k}"][:, 0].sum()) for k in range(7)) > 100          # the frames do decode to joints
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
