@@ -184,3 +184,33 @@ def test_host_frame_validation():
                 np.zeros((0, 64, 48, 3), np.uint8), np.zeros((2, 64, 48, 3), np.int32), np.zeros((2, 64, 48, 4), np.uint8)):
         with pytest.raises(ValueError):
             val(bad, 64, 48, 4)
+
+
+def test_fits_executor_and_general_depthwise_folding():
+    """Host logic behind the non-default reference arguments: a variable set with other head widths is recognised as not
+    loadable into the 14 / 26 executor, and a separable layer with a 5x5 depthwise kernel folds to [25][cin] taps."""
+    from lightweight_openpose_b200 import graph
+    entries, _ = checkpoint.read_index(checkpoint.default_index_prefix() + ".index")
+    v = checkpoint.synthetic_variables(entries)
+    assert graph.fits_executor(v)
+    heads = [l for l in graph.LAYERS if l.note in ("heatmaps1", "heatmaps2", "pafs1", "pafs2")]
+    assert len(heads) == 4 and sorted(l.cout for l in heads) == [14, 14, 26, 26]
+    w = dict(v)
+    k = w[heads[0].name + "/kernel"]
+    w[heads[0].name + "/kernel"] = np.zeros(k.shape[:3] + (19,), np.float32)
+    assert not graph.fits_executor(w)
+    missing = dict(v)
+    del missing[heads[1].name + "/kernel"]
+    assert not graph.fits_executor(missing)
+
+    rng = np.random.default_rng(0)
+    cin, cout = 6, 10
+    layer = graph.Layer(-1, graph.KIND_SEPARABLE, "T/separable_conv2d", None, cin, cout, 1, 1, 1, graph.ACT_ELU, False, dw_k=5)
+    vv = {"T/separable_conv2d/depthwise_kernel": rng.standard_normal((5, 5, cin, 1)).astype(np.float32),
+          "T/separable_conv2d/pointwise_kernel": rng.standard_normal((1, 1, cin, cout)).astype(np.float32)}
+    f = graph.fold_layer(layer, vv)
+    assert f.dw.shape == (25, cin) and f.w.shape == (cout, 1, cin) and f.b.shape == (cout,)
+    assert np.array_equal(f.dw[7], vv["T/separable_conv2d/depthwise_kernel"][1, 2, :, 0])      # tap index = dy * 5 + dx
+    assert np.array_equal(f.w[:, 0, :], vv["T/separable_conv2d/pointwise_kernel"][0, 0].T)
+    with pytest.raises(AssertionError):
+        graph.fold_layer(graph.Layer(-1, graph.KIND_SEPARABLE, "T/separable_conv2d", None, cin, cout, 1, 1, 1, graph.ACT_ELU, False), vv)
