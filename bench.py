@@ -502,8 +502,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     lo, hi = replicas.shard_bounds(G, world, rank)
     b = hi - lo
     # steps in flight per GPU: small slices leave more of every kernel's fill / drain and of the latency-bound decode
-    # chain exposed, and more concurrent steps fill those gaps (measured: 4 lanes at 256 frames, 16 at 32)
-    lanes = args.lanes if args.lanes > 0 else max(3, min(16, 1024 // b))
+    # chain exposed, and more concurrent steps fill those gaps (measured: 4 lanes at 256 frames; at 32 frames 16 / 24 / 32 lanes
+    # give 33.4 / 33.9 / 33.8 k images/s)
+    lanes = args.lanes if args.lanes > 0 else max(3, min(24, 1024 // b))
     # the result ring lives in /dev/shm (~16 kB per frame and slot): fall back to a shallow pipeline on a box whose
     # tmpfs could not hold it
     depth = args.depth
