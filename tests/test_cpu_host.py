@@ -214,3 +214,12 @@ def test_fits_executor_and_general_depthwise_folding():
     assert np.array_equal(f.w[:, 0, :], vv["T/separable_conv2d/pointwise_kernel"][0, 0].T)
     with pytest.raises(AssertionError):
         graph.fold_layer(graph.Layer(-1, graph.KIND_SEPARABLE, "T/separable_conv2d", None, cin, cout, 1, 1, 1, graph.ACT_ELU, False), vv)
+
+
+def test_every_entry_point_is_mapped_in_integration_md():
+    """INTEGRATION.md names, for every function include/lwop.h declares, the reference lines it replaces."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8") as fh:
+        text = fh.read()
+    missing = [f for f in _lib.header_functions() if f"`{f}`" not in text]
+    assert not missing, missing
